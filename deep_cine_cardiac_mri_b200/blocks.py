@@ -1,0 +1,281 @@
+"""Block-tier drop-ins: the SENSE / data-consistency methods of the reference's
+model classes, re-expressed over the fused kernels with unchanged signatures.
+
+Every function takes the reference module instance as `self` (they are bound
+onto the reference classes by `patch.patch_reference()`), so learnable state
+(`lambda_reg`, `Softplus`, the regulariser sub-modules) stays where the
+reference's checkpoints expect it.  The regularisers (U-Net / MWCNN / CRNN) are
+called exactly as the reference calls them.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from . import functional as F
+
+
+# --------------------------------------------------------------------------- #
+# shared operator helpers
+# --------------------------------------------------------------------------- #
+def sens_expand(self, x: torch.Tensor, sens_maps: torch.Tensor) -> torch.Tensor:
+    """VarNetBlock.sens_expand (models/varnet.py:181-185), CineNetBlock (cinenet.py:106-110),
+    CineNet_RNN (recurrent_cinenet.py:59-63): fft2c(S * x).  x (b,t,1,h,w,2) -> (b,t,c,h,w,2)."""
+    return ops.sens_expand(x, sens_maps)
+
+
+def sens_reduce(self, x: torch.Tensor, sens_maps: torch.Tensor) -> torch.Tensor:
+    """VarNetBlock.sens_reduce (varnet.py:187-194) & copies: sum_c conj(S) ifft2c(k), keepdim."""
+    return ops.sens_reduce(x, sens_maps).unsqueeze(2)
+
+
+def _xfyf(self, image_combined: torch.Tensor, run_models) -> torch.Tensor:
+    """Temporal head/tail of xfyf_transform (varnet.py:196-241, cinenet.py:174-219) around the
+    untouched regularisers.  image_combined (b,t,h,w,2) -> (b,t,1,h,w,2)."""
+    xf = self.dynamic_type == 'XF'
+    x, mean = ops.TemporalPreFn.apply(image_combined, xf)           # mean-subtract (+ fft1c over t)
+    out = run_models(x)                                             # (b,t,1,h,w,2)
+    return ops.TemporalPostFn.apply(out.squeeze(2), mean, xf).unsqueeze(2)
+
+
+def varnet_xfyf_transform(self, image_combined: torch.Tensor) -> torch.Tensor:
+    """VarNetBlock.xfyf_transform (varnet.py:196-241)."""
+    b, t, h, w, ch = image_combined.shape
+
+    def run(x):
+        xf = x.permute(0, 2, 3, 1, 4).reshape(b * h, 1, w, t, 2)
+        yf = x.permute(0, 3, 2, 1, 4).reshape(b * w, 1, h, t, 2)
+        if self.weight_sharing:
+            xf, yf = self.model(xf), self.model(yf)
+        else:
+            model_xf, model_yf = self.model
+            xf, yf = model_xf(xf), model_yf(yf)
+        xf_r = xf.view(b, h, 1, w, t, 2).permute(0, 4, 2, 1, 3, 5)
+        yf_r = yf.view(b, w, 1, h, t, 2).permute(0, 4, 2, 3, 1, 5)
+        return 0.5 * (xf_r + yf_r)
+
+    return _xfyf(self, image_combined, run)
+
+
+def cinenet_xfyf_transform(self, image_combined: torch.Tensor) -> torch.Tensor:
+    """CineNetBlock.xfyf_transform (cinenet.py:174-219)."""
+    b, t, h, w, ch = image_combined.shape
+
+    def run(x):
+        xf = x.permute(0, 2, 4, 3, 1).reshape(b * h, 2, w, t)
+        yf = x.permute(0, 3, 4, 2, 1).reshape(b * w, 2, h, t)
+        if self.weight_sharing:
+            xf, yf = self.model(xf), self.model(yf)
+        else:
+            model_xf, model_yf = self.model
+            xf, yf = model_xf(xf), model_yf(yf)
+        xf_r = xf.view(b, h, 1, 2, w, t).permute(0, 5, 2, 1, 4, 3)
+        yf_r = yf.view(b, w, 1, 2, h, t).permute(0, 5, 2, 4, 1, 3)
+        return 0.5 * (xf_r + yf_r)
+
+    return _xfyf(self, image_combined, run)
+
+
+# --------------------------------------------------------------------------- #
+# VarNet
+# --------------------------------------------------------------------------- #
+def varnet_block_forward(self, current_kspace, ref_kspace, mask, sens_maps):
+    """VarNetBlock.forward (varnet.py:244-282): A^H -> regulariser -> A fused with the soft-DC blend."""
+    image_combined = ops.sens_reduce(current_kspace, sens_maps).unsqueeze(2)
+
+    if self.dynamic_type in ['XF', 'XT']:
+        model_out = self.xfyf_transform(image_combined.squeeze(2))
+    elif self.dynamic_type == '2D':
+        model_out = self.model(image_combined.squeeze(0)).unsqueeze(0)
+    elif self.dynamic_type == '3D':
+        model_out = self.model(image_combined.permute(0, 2, 1, 3, 4, 5)).permute(0, 2, 1, 3, 4, 5)
+    else:
+        raise ValueError(f"unknown dynamic_type {self.dynamic_type!r}")
+
+    v = self.Softplus(self.lambda_reg)
+    return ops.sens_expand(model_out, sens_maps, ops.EXPAND_DC, ref=ref_kspace, mask=mask, v=v)
+
+
+def varnet_forward(self, masked_kspace: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """VarNet.forward (varnet.py:143-151); the clone of masked_kspace is not needed (ops never mutate)."""
+    sens_maps = self.sens_net(masked_kspace, mask)
+    kspace_pred = masked_kspace
+    for cascade in self.cascades:
+        kspace_pred = cascade(kspace_pred, masked_kspace, mask, sens_maps)
+    return F.complex_abs(ops.sens_reduce(kspace_pred, sens_maps))
+
+
+def _sens_pre(masked_kspace, mask):
+    """ACS low-pass of the time mean + ifft2c (varnet.py:64-74 / xpdnet.py:75-85); the window is found
+    on the device (no nonzero() host syncs)."""
+    b, t, c, h, w, _ = masked_kspace.shape
+    x = ops.AcsMeanFn.apply(masked_kspace, ops._mask_u8(mask, b, t, h))
+    return ops.fft2c(x, "ortho", inverse=True)                       # (b,c,h,w,2)
+
+
+def varnet_sens_model_forward(self, masked_kspace: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """SensitivityModel.forward (varnet.py:62-86)."""
+    x = _sens_pre(masked_kspace, mask)
+    x, b = self.chans_to_batch_dim(x)
+    x = self.norm_unet(x)
+    x = self.batch_chans_to_chan_dim(x, b)
+    return ops.RssNormalizeFn.apply(x).unsqueeze(1)
+
+
+def xpdnet_sens_model_forward(self, masked_kspace: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """xpdnet.SensitivityModel.forward (xpdnet.py:73-100)."""
+    x = _sens_pre(masked_kspace, mask)
+    b, x = self.chans_to_batch_dim(x)
+    x_temp = x
+    x = self.unet_model(x)
+    if self.res_connection:
+        x = x + x_temp
+    x = self.batch_chans_to_chan_dim(x, b)
+    return ops.RssNormalizeFn.apply(x).unsqueeze(1)
+
+
+def divide_root_sum_of_squares(self, x: torch.Tensor) -> torch.Tensor:
+    """SensitivityModel.divide_root_sum_of_squares (varnet.py:58-59)."""
+    return ops.RssNormalizeFn.apply(x)
+
+
+# --------------------------------------------------------------------------- #
+# VarNet_RNN (recurrent_varnet.py:65-90): (b,2,h,w,t) image layout
+# --------------------------------------------------------------------------- #
+def varnet_rnn_sens_expand(self, x, sens_maps):
+    return ops.sens_expand(x.permute(0, 4, 2, 3, 1), sens_maps)
+
+
+def varnet_rnn_sens_reduce(self, x, sens_maps):
+    return ops.sens_reduce(x, sens_maps).permute(0, 4, 2, 3, 1)
+
+
+def varnet_rnn_data_consistency(self, x, ref_kspace, mask, sens_maps):
+    v = self.Softplus(self.lambda_reg)
+    dc = ops.sens_expand(x.permute(0, 4, 2, 3, 1), sens_maps, ops.EXPAND_DC, ref=ref_kspace, mask=mask, v=v)
+    return ops.sens_reduce(dc, sens_maps).permute(0, 4, 2, 3, 1)
+
+
+# --------------------------------------------------------------------------- #
+# CineNet (cinenet.py:121-171, recurrent_cinenet.py:74-124)
+# --------------------------------------------------------------------------- #
+def h_operator(self, x: torch.Tensor, mask: torch.Tensor, sens_maps: torch.Tensor) -> torch.Tensor:
+    """HOperator: A^H M A x + softplus(lambda) x, k-space kept on chip.  x (b,t,1,h,w,2)."""
+    v = self.Softplus(self.lambda_reg)
+    return ops.normal_op(x.squeeze(2), sens_maps, mask, v).unsqueeze(2)
+
+
+def conj_grad(self, x, b, mask, sens_maps, CG_iters: int):
+    """ConjGrad (cinenet.py:136-171).  alpha/beta are constants for autograd exactly as in the
+    reference (`.item()`), but they stay on the device: no host synchronisation."""
+    v = self.Softplus(self.lambda_reg)
+    squeeze = x.dim() == 6
+    xs = x.squeeze(2) if squeeze else x
+    bs = b.squeeze(2) if squeeze else b
+    if torch.is_grad_enabled() and (xs.requires_grad or bs.requires_grad or v.requires_grad):
+        out = _cg_autograd(xs, bs, mask, sens_maps, v, CG_iters)
+    else:
+        out = _cg_inference(xs, bs, mask, sens_maps, v, CG_iters)
+    return out.unsqueeze(2) if squeeze else out
+
+
+def _cg_autograd(x, b, mask, sens, v, iters):
+    H = lambda z: ops.normal_op(z, sens, mask, v)                    # noqa: E731
+    r = b - H(x)
+    p = r.clone()
+    rs_old = ops.raw_dot(r.detach().contiguous(), r.detach().contiguous())
+    for _ in range(iters):
+        d = H(p)
+        pd = ops.raw_dot(p.detach().contiguous(), d.detach().contiguous())
+        alpha = rs_old / pd
+        x = x + alpha * p
+        r = r - alpha * d
+        rs_new = ops.raw_dot(r.detach().contiguous(), r.detach().contiguous())
+        p = r + (rs_new / rs_old) * p
+        rs_old = rs_new
+    return x
+
+
+def _cg_inference(x, b, mask, sens, v, iters):
+    from . import _lib
+    lib = _lib.lib()
+    st = ops._stream
+    P = ops._p
+    x = ops._f32c(x).clone()
+    b = ops._f32c(b)
+    if sens.dim() == 6:
+        sens = sens.squeeze(1)
+    sens = ops._f32c(sens)
+    bb, t, h, w, _ = x.shape
+    m8 = ops._mask_u8(mask, bb, t, h)
+    vd = v.detach().reshape(1).to(device=x.device, dtype=torch.float32)
+    n = x.numel()
+    dev = x.device
+    scal = torch.empty(4, dtype=torch.float32, device=dev)           # rs_old, pd, rs_new
+    scratch = torch.empty(1024, dtype=torch.float32, device=dev)
+    rs_old, pd, rs_new = scal[0:1], scal[1:2], scal[2:3]
+
+    def H(z):
+        if ops.normal_op_supported(h, w):
+            return ops.raw_normal_op(z, sens, m8, vd)
+        k = ops.raw_sens_expand(z, sens, ops.EXPAND_MASK, None, m8, None, 1)
+        return ops.raw_axpby(ops.raw_sens_reduce(k, sens, norm=1), z, vd, 1.0)
+
+    r = ops.raw_axpby(b, H(x), None, -1.0)                           # r = b - Hx
+    p = r.clone()
+    _lib.check(lib.b2s_dot(P(r), P(r), P(rs_old), n, P(scratch), st()), "dot")
+    for _ in range(iters):
+        d = H(p)
+        _lib.check(lib.b2s_dot(P(p), P(d), P(pd), n, P(scratch), st()), "dot")
+        _lib.check(lib.b2s_axpy_ratio(P(x), P(p), P(rs_old), P(pd), 1.0, n, st()), "axpy")     # x += alpha p
+        _lib.check(lib.b2s_axpy_ratio(P(r), P(d), P(rs_old), P(pd), -1.0, n, st()), "axpy")    # r -= alpha d
+        _lib.check(lib.b2s_dot(P(r), P(r), P(rs_new), n, P(scratch), st()), "dot")
+        _lib.check(lib.b2s_xpay_ratio(P(p), P(r), P(rs_new), P(rs_old), n, st()), "xpay")      # p = r + beta p
+        rs_old, rs_new = rs_new, rs_old
+    return x
+
+
+def cinenet_forward(self, masked_kspace, mask, sens_maps):
+    """CineNet.forward (cinenet.py:61-73)."""
+    image_pred = ops.sens_reduce(masked_kspace, sens_maps).unsqueeze(2)
+    image_ref = image_pred
+    for cascade in self.cascades:
+        image_pred = cascade(image_pred, image_ref, mask, sens_maps)
+    return F.complex_abs(image_pred.squeeze(2))
+
+
+# --------------------------------------------------------------------------- #
+# XPDNet operators (xpdnet.py:104-167)
+# --------------------------------------------------------------------------- #
+def forward_operator_forward(self, image, mask, sens_maps, buffer_size: int):
+    """ForwardOperator.forward: acts on buffer channels 0 and buffer_size; optional `* mask + 0.0`."""
+    img = torch.stack([image[..., 0], image[..., buffer_size]], dim=-1)
+    if self.masked:
+        return ops.sens_expand(img, sens_maps, ops.EXPAND_MASK, mask=mask)
+    return ops.sens_expand(img, sens_maps)
+
+
+def backward_operator_forward(self, kspace, mask, sens_maps, buffer_size: int):
+    """BackwardOperator.forward: optional mask, ifft2c, conj(S) multiply, coil sum (keepdim)."""
+    if kspace.shape[-1] != 2:
+        kspace = torch.stack([kspace[..., 0], kspace[..., buffer_size]], dim=-1)
+    return ops.sens_reduce(kspace, sens_maps, mask=mask if self.masked else None).unsqueeze(2)
+
+
+def xpd_temporal_fft(x: torch.Tensor, n_ch: int) -> torch.Tensor:
+    """xpdnet.py:465-467: packed (b,t,h,w,2n) -> ifftshift(fft(fftshift(.,1),t,1,'ortho'),1), packed."""
+    b, t, h, w, _ = x.shape
+    z = torch.stack([x[..., :n_ch], x[..., n_ch:]], dim=-1)          # (b,t,h,w,n,2)
+    z = z.permute(0, 2, 3, 4, 1, 5)                                   # (b,h,w,n,t,2): FFT dim at -2
+    z = ops.fft1c(z.contiguous(), "ortho", False, shift_in=t // 2, shift_out=(t + 1) // 2)
+    z = z.permute(0, 4, 1, 2, 3, 5)
+    return torch.cat([z[..., 0], z[..., 1]], dim=-1)
+
+
+def xpd_temporal_ifft(x: torch.Tensor, n_ch: int) -> torch.Tensor:
+    """xpdnet.py:499-501: fftshift(ifft(ifftshift(.,1),t,1,'ortho'),1) == ifft1c over t."""
+    b, t, h, w, _ = x.shape
+    z = torch.stack([x[..., :n_ch], x[..., n_ch:]], dim=-1).permute(0, 2, 3, 4, 1, 5)
+    z = ops.fft1c(z.contiguous(), "ortho", True)
+    z = z.permute(0, 4, 1, 2, 3, 5)
+    return torch.cat([z[..., 0], z[..., 1]], dim=-1)

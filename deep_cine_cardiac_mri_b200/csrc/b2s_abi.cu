@@ -1,0 +1,16 @@
+// Version / error plumbing of the C ABI (include/b200sense.h).
+#include <stdarg.h>
+#include "b2s_common.cuh"
+
+namespace b2s {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace b2s
+
+extern "C" int b2s_version(void) { return 100; }
+extern "C" const char* b2s_last_error(void) { return b2s::g_err; }

@@ -1,0 +1,171 @@
+// Fused single-pass SENSE operators on the plan sizes (200 x 200) and their
+// composition from the generic kernels for every other size.
+#include "b2s_common.cuh"
+#include "sense_functors.cuh"
+#include "fft2_kernel.cuh"
+
+using namespace b2s;
+
+namespace {
+
+typedef Plan<200, 200> P200;
+
+template <class P, class Pro, class Epi>
+int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st) {
+  if (n_images <= 0) return B2S_OK;
+  if (2 * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
+  auto kern = fft2_half_kernel<P, Pro, Epi>;
+  static bool configured = false;            // per instantiation; idempotent attribute
+  if (!configured) {
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<P>::SMEM_BYTES));
+    configured = true;
+  }
+  kern<<<(unsigned)(2 * n_images), P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale);
+  return check_launch("fft2_half_kernel");
+}
+
+}  // namespace
+
+extern "C" int b2s_has_fused_plan(int h, int w) { return (h == 200 && w == 200) ? 1 : 0; }
+
+extern "C" size_t b2s_scratch_bytes(int b, int t, int c, int h, int w) {
+  if (b2s_has_fused_plan(h, w)) return 0;
+  return (size_t)b * t * c * h * w * 2 * sizeof(float);
+}
+
+extern "C" int b2s_fft2c(const float* in, float* out, int64_t n_images, int h, int w, int inverse,
+                         int norm, void* stream) {
+  if (!in || !out || h <= 0 || w <= 0 || n_images < 0 || bad_norm(norm)) return fail(B2S_EINVAL, "b2s_fft2c: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float scale = norm_scale(h, w, inverse, norm);
+  if (h == 200 && w == 200) {
+    const long long hw = 40000;
+    const float s = scale * centre_sign<P200>();
+    if (inverse) {
+      ProPlain<200, true> pro{(const cfloat*)in, hw};
+      EpiPlain<200, true> epi{(cfloat*)out, hw};
+      return launch_fused<P200>(pro, epi, s, n_images, st);
+    }
+    ProPlain<200, false> pro{(const cfloat*)in, hw};
+    EpiPlain<200, false> epi{(cfloat*)out, hw};
+    return launch_fused<P200>(pro, epi, s, n_images, st);
+  }
+  return generic_fft2(in, out, n_images, h, w, inverse, scale, st);
+}
+
+extern "C" int b2s_sens_expand(const float* image, const float* sens, float* kspace, const float* ref,
+                               const uint8_t* mask, const float* v, int mode, int b, int t, int c,
+                               int h, int w, int norm, void* scratch, size_t scratch_bytes, void* stream) {
+  (void)scratch; (void)scratch_bytes;
+  if (!image || !sens || !kspace || b < 0 || t < 0 || c < 0 || bad_norm(norm) || mode < 0 || mode > 3)
+    return fail(B2S_EINVAL, "b2s_sens_expand: bad argument");
+  if ((mode >= 1 && !mask) || (mode >= 2 && !ref) || (mode == 2 && !v))
+    return fail(B2S_EINVAL, "b2s_sens_expand: mode needs mask/ref/v");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)b * t * c;
+  const float scale = norm_scale(h, w, 0, norm);
+  if (h == 200 && w == 200) {
+    const long long hw = 40000;
+    const float s = scale * centre_sign<P200>();
+    ProExpand<200> pro{(const cfloat*)image, (const cfloat*)sens, t, c, hw};
+#define B2S_RUN(M)                                                                            \
+  {                                                                                           \
+    EpiKspace<200, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, h, hw};            \
+    return launch_fused<P200>(pro, epi, s, n, st);                                            \
+  }
+    switch (mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) case 2: B2S_RUN(2) default: B2S_RUN(3) }
+#undef B2S_RUN
+  }
+  // generic sizes: S*x -> kspace, FFT in place, epilogue in place
+  int rc = launch_expand_product(image, sens, kspace, b, t, c, (int64_t)h * w, st);
+  if (rc) return rc;
+  rc = generic_fft2(kspace, kspace, n, h, w, 0, scale, st);
+  if (rc) return rc;
+  if (mode == 0) return B2S_OK;
+  return launch_kspace_epilogue(kspace, ref, mask, v, mode, (int64_t)b * t, c, h, w, st);
+}
+
+extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* out, const uint8_t* mask,
+                               const float* v, int weight_mode, int over_frames, int b, int t, int c,
+                               int h, int w, int norm, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!kspace || !mult || !out || b < 0 || t < 0 || c < 0 || bad_norm(norm) || weight_mode < 0 || weight_mode > 2)
+    return fail(B2S_EINVAL, "b2s_sens_reduce: bad argument");
+  if ((weight_mode >= 1 && !mask) || (weight_mode == 2 && !v))
+    return fail(B2S_EINVAL, "b2s_sens_reduce: weight mode needs mask/v");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)b * t * c;
+  const int64_t hw = (int64_t)h * w;
+  const float scale = norm_scale(h, w, 1, norm);
+  const int64_t out_images = over_frames ? (int64_t)b * c : (int64_t)b * t;
+  if (out_images == 0) return B2S_OK;
+  if (h == 200 && w == 200) {
+    B2S_CUDA(cudaMemsetAsync(out, 0, (size_t)out_images * hw * 2 * sizeof(float), st));
+    if (n == 0) return B2S_OK;
+    const float s = scale * centre_sign<P200>();
+    EpiReduce<200> epi;
+    epi.out = (cfloat*)out; epi.mult = (const cfloat*)mult; epi.T = t; epi.C = c;
+    if (!over_frames) { epi.os_b = t * hw; epi.os_t = hw; epi.os_c = 0; epi.ms_b = c * hw; epi.ms_t = 0; epi.ms_c = hw; }
+    else              { epi.os_b = c * hw; epi.os_t = 0; epi.os_c = hw; epi.ms_b = t * hw; epi.ms_t = hw; epi.ms_c = 0; }
+#define B2S_RUN(M)                                                            \
+  {                                                                           \
+    ProKspace<200, M> pro{(const cfloat*)kspace, mask, v, c, h, hw};          \
+    return launch_fused<P200>(pro, epi, s, n, st);                            \
+  }
+    switch (weight_mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) default: B2S_RUN(2) }
+#undef B2S_RUN
+  }
+  // generic sizes: (row weight) -> IFFT into scratch -> conj-multiply + reduce
+  const size_t need = (size_t)n * hw * 2 * sizeof(float);
+  if (n > 0 && (!scratch || scratch_bytes < need)) return fail(B2S_EINVAL, "b2s_sens_reduce: scratch too small (see b2s_scratch_bytes)");
+  float* y = (float*)scratch;
+  int rc = B2S_OK;
+  const float* src = kspace;
+  if (weight_mode) {
+    rc = launch_row_weight(kspace, y, mask, v, weight_mode, (int64_t)b * t, c, h, w, st);
+    if (rc) return rc;
+    src = y;
+  }
+  if (n > 0) {
+    rc = generic_fft2(src, y, n, h, w, 1, scale, st);
+    if (rc) return rc;
+  }
+  return launch_coil_reduce(y, mult, out, over_frames, b, t, c, hw, st);
+}
+
+extern "C" size_t b2s_dc_step_ws_bytes(int b, int t, int c, int h, int w) {
+  const size_t K = (size_t)b * t * c * h * w * 8, I = (size_t)b * t * h * w * 8, S = (size_t)b * c * h * w * 8;
+  const size_t M = ((size_t)b * t * h + 255) / 256 * 256;
+  return 3 * K + I + S + M + 256 + b2s_scratch_bytes(b, t, c, h, w);
+}
+
+extern "C" int b2s_dc_step_host(const float* kspace_host, const float* ref_host, const float* sens_host,
+                                const uint8_t* mask_host, float v_value, float* out_host, int b, int t,
+                                int c, int h, int w, void* ws, size_t ws_bytes, void* stream) {
+  if (!kspace_host || !ref_host || !sens_host || !mask_host || !out_host || !ws)
+    return fail(B2S_EINVAL, "b2s_dc_step_host: null pointer");
+  if (ws_bytes < b2s_dc_step_ws_bytes(b, t, c, h, w)) return fail(B2S_EINVAL, "b2s_dc_step_host: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t K = (size_t)b * t * c * h * w * 8, I = (size_t)b * t * h * w * 8, S = (size_t)b * c * h * w * 8;
+  const size_t M = ((size_t)b * t * h + 255) / 256 * 256;
+  char* p = (char*)ws;
+  float* dk = (float*)p; p += K;
+  float* dref = (float*)p; p += K;
+  float* dout = (float*)p; p += K;
+  float* dimg = (float*)p; p += I;
+  float* dsens = (float*)p; p += S;
+  uint8_t* dmask = (uint8_t*)p; p += M;
+  float* dv = (float*)p; p += 256;
+  void* scratch = p;
+  const size_t sb = b2s_scratch_bytes(b, t, c, h, w);
+  B2S_CUDA(cudaMemcpyAsync(dk, kspace_host, K, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(dref, ref_host, K, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(dsens, sens_host, S, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(dmask, mask_host, (size_t)b * t * h, cudaMemcpyHostToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(dv, &v_value, sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = b2s_sens_reduce(dk, dsens, dimg, nullptr, nullptr, 0, 0, b, t, c, h, w, B2S_NORM_ORTHO, scratch, sb, st);
+  if (rc) return rc;
+  rc = b2s_sens_expand(dimg, dsens, dout, dref, dmask, dv, B2S_EXPAND_DC, b, t, c, h, w, B2S_NORM_ORTHO, scratch, sb, st);
+  if (rc) return rc;
+  B2S_CUDA(cudaMemcpyAsync(out_host, dout, K, cudaMemcpyDeviceToHost, st));
+  return B2S_OK;
+}

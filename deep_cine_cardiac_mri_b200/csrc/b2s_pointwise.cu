@@ -1,0 +1,467 @@
+// Memory-bound element-wise / small-reduction kernels of the SENSE path:
+// stand-alone DC blend (+backward), the fastMRI complex helpers, RSS, the
+// SensitivityModel pre/post ops, the xfyf temporal head/tail and the CG vector
+// kernels.  All are grid-stride, 64/128-bit vectorised, one pass over HBM.
+#include "b2s_common.cuh"
+#include "fft2_core.cuh"
+
+using namespace b2s;
+
+namespace {
+
+constexpr int NT = 256;
+inline unsigned grid_for(long long n, int per_block = NT, long long cap = 148LL * 16) {
+  long long g = (n + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (unsigned)g;
+}
+#define GRID_STRIDE(i, n) for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  if (wid == 0) for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;   // valid in thread 0
+}
+
+// ---------------- generic-size fallbacks of the fused operators ---------------- //
+__global__ void expand_product_kernel(const cfloat* img, const cfloat* sens, cfloat* out, int T, int C,
+                                      long long hw, long long n) {
+  GRID_STRIDE(i, n) {
+    const long long pix = i % hw, im = i / hw, c = im % C, bt = im / C, b = bt / T;
+    const cfloat a = img[bt * hw + pix], s = sens[(b * C + c) * hw + pix];
+    out[i] = make_c(a.x * s.x - a.y * s.y, a.x * s.y + a.y * s.x);
+  }
+}
+
+__global__ void kspace_epilogue_kernel(cfloat* k, const cfloat* ref, const uint8_t* mask, const float* vptr,
+                                       int mode, int C, int H, int W, long long n) {
+  const float v = (mode == 2) ? *vptr : 0.f;
+  GRID_STRIDE(i, n) {
+    const long long row = i / W, y = row % H, bt = row / H / C;
+    const bool m = mask[bt * H + y] != 0;
+    cfloat z = k[i];
+    if (mode == 1) { if (!m) z = make_c(0.f, 0.f); }
+    else if (mode == 2) { if (m) { const cfloat r = ref[i]; z = make_c((z.x + v * r.x) / (1.f + v), (z.y + v * r.y) / (1.f + v)); } }
+    else { const cfloat r = ref[i]; if (!m) z = make_c(0.f, 0.f); z = make_c(z.x - r.x, z.y - r.y); }
+    k[i] = z;
+  }
+}
+
+__global__ void row_weight_kernel(const cfloat* k, cfloat* out, const uint8_t* mask, const float* vptr,
+                                  int wmode, int C, int H, int W, long long n) {
+  float wa = 0.f, wb = 1.f;
+  if (wmode == 2) { const float v = *vptr; wa = 1.f; wb = -v / (1.f + v); }
+  GRID_STRIDE(i, n) {
+    const long long row = i / W, y = row % H, bt = row / H / C;
+    const float wgt = wa + wb * (float)mask[bt * H + y];
+    const cfloat z = k[i];
+    out[i] = make_c(z.x * wgt, z.y * wgt);
+  }
+}
+
+__global__ void coil_reduce_kernel(const cfloat* y, const cfloat* mult, cfloat* out, int over_frames, int T,
+                                   int C, long long hw, long long n_out) {
+  GRID_STRIDE(i, n_out) {
+    const long long pix = i % hw, oi = i / hw;     // oi = b*T+t (coil sum) or b*C+c (frame sum)
+    float ar = 0.f, ai = 0.f;
+    if (!over_frames) {
+      const long long b = oi / T;
+      for (int c = 0; c < C; ++c) {
+        const cfloat v = y[(oi * C + c) * hw + pix], s = mult[(b * C + c) * hw + pix];
+        ar += v.x * s.x + v.y * s.y; ai += v.y * s.x - v.x * s.y;
+      }
+    } else {
+      const long long b = oi / C, c = oi % C;
+      for (int t = 0; t < T; ++t) {
+        const cfloat v = y[((b * T + t) * C + c) * hw + pix], s = mult[(b * T + t) * hw + pix];
+        ar += v.x * s.x + v.y * s.y; ai += v.y * s.x - v.x * s.y;
+      }
+    }
+    out[i] = make_c(ar, ai);
+  }
+}
+
+// ------------------------------- DC blend ---------------------------------- //
+__global__ void dc_blend_kernel(const float4* k, const float4* ref, const uint8_t* mask, const float* vptr,
+                                float4* out, int C, int H, int W2, long long n4) {
+  const float v = *vptr;
+  GRID_STRIDE(i, n4) {                                 // one float4 = 2 complex
+    const long long row = i / W2, y = row % H, bt = row / H / C;
+    float4 z = k[i];
+    if (mask[bt * H + y]) {
+      const float4 r = ref[i];
+      z.x = (z.x + v * r.x) / (1.f + v); z.y = (z.y + v * r.y) / (1.f + v);
+      z.z = (z.z + v * r.z) / (1.f + v); z.w = (z.w + v * r.w) / (1.f + v);
+    }
+    out[i] = z;
+  }
+}
+
+__global__ void dc_blend_bwd_kernel(const float4* g, const float4* outv, const float4* ref, const uint8_t* mask,
+                                    const float* vptr, float4* gk, float4* gref, float* gv, int C, int H, int W2,
+                                    long long n4) {
+  const float v = *vptr, eta = v / (1.f + v), inv1 = 1.f / (1.f + v);
+  float acc = 0.f;
+  GRID_STRIDE(i, n4) {
+    const long long row = i / W2, y = row % H, bt = row / H / C;
+    const float4 gg = g[i];
+    const bool m = mask[bt * H + y] != 0;
+    const float a = m ? (1.f - eta) : 1.f, bb = m ? eta : 0.f;
+    if (gk) gk[i] = make_float4(gg.x * a, gg.y * a, gg.z * a, gg.w * a);
+    if (gref) gref[i] = make_float4(gg.x * bb, gg.y * bb, gg.z * bb, gg.w * bb);
+    if (gv && m) {
+      const float4 r = ref[i], o = outv[i];
+      acc += (gg.x * (r.x - o.x) + gg.y * (r.y - o.y) + gg.z * (r.z - o.z) + gg.w * (r.w - o.w)) * inv1;
+    }
+  }
+  if (gv) {
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) atomicAdd(gv, acc);
+  }
+}
+
+// ---------------------------- complex helpers ------------------------------ //
+struct MulDims { int nd; long long shape[6], sa[6], sb[6]; };
+
+__global__ void complex_mul_kernel(const cfloat* a, const cfloat* b, cfloat* out, MulDims d, int conj_b, long long n) {
+  GRID_STRIDE(i, n) {
+    long long rem = i, oa = 0, ob = 0;
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+      if (k < d.nd) { const long long idx = rem % d.shape[k]; rem /= d.shape[k]; oa += idx * d.sa[k]; ob += idx * d.sb[k]; }
+    }
+    const cfloat x = a[oa]; cfloat y = b[ob];
+    if (conj_b) y.y = -y.y;
+    out[i] = make_c(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
+  }
+}
+
+__global__ void complex_conj_kernel(const cfloat* in, cfloat* out, long long n) {
+  GRID_STRIDE(i, n) { const cfloat v = in[i]; out[i] = make_c(v.x, -v.y); }
+}
+
+__global__ void complex_abs_kernel(const cfloat* in, float* out, long long n, int squared) {
+  GRID_STRIDE(i, n) { const cfloat v = in[i]; const float s = v.x * v.x + v.y * v.y; out[i] = squared ? s : sqrtf(s); }
+}
+
+__global__ void rss_kernel(const float* in, float* out, long long outer, long long r, long long inner, int is_complex) {
+  const long long n = outer * inner;
+  GRID_STRIDE(i, n) {
+    const long long o = i / inner, p = i % inner;
+    float acc = 0.f;
+    if (is_complex) {
+      const cfloat* z = reinterpret_cast<const cfloat*>(in);
+      for (long long k = 0; k < r; ++k) { const cfloat v = z[(o * r + k) * inner + p]; acc += v.x * v.x + v.y * v.y; }
+    } else {
+      for (long long k = 0; k < r; ++k) { const float v = in[(o * r + k) * inner + p]; acc += v * v; }
+    }
+    out[i] = sqrtf(acc);
+  }
+}
+
+// ------------------------- SensitivityModel pre/post ----------------------- //
+// ACS window exactly as models/varnet.py:64-68 on frame 0 of each batch element.
+__device__ __forceinline__ void acs_window(const uint8_t* m0, int H, int& pad, int& nlf) {
+  const int cent = H / 2;
+  int left = -1, right = H;
+  for (int y = 0; y < cent; ++y) if (m0[y] == 0) left = y;              // last zero in [:cent]
+  for (int y = H - 1; y >= cent; --y) if (m0[y] == 0) right = y;        // first zero in [cent:]
+  nlf = right - left;
+  pad = (H - nlf + 1) / 2;
+}
+
+__global__ void acs_mean_kernel(const cfloat* k, const uint8_t* mask, cfloat* out, int32_t* window_out, int T, int C,
+                                int H, int W) {
+  // blockIdx.y = batch element; the window is computed once per block
+  __shared__ int s_pad, s_nlf;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    int pad, nlf; acs_window(mask + (long long)b * T * H, H, pad, nlf);
+    s_pad = pad; s_nlf = nlf;
+    if (window_out && blockIdx.x == 0) { window_out[2 * b] = pad; window_out[2 * b + 1] = nlf; }
+  }
+  __syncthreads();
+  const int pad = s_pad, nlf = s_nlf;
+  const long long hw = (long long)H * W, per_b = (long long)C * hw;
+  const float invT = 1.f / (float)T;
+  GRID_STRIDE(i, per_b) {
+    const long long c = i / hw, yx = i % hw;
+    const int y = (int)(yx / W);
+    cfloat acc = make_c(0.f, 0.f);
+    if (y >= pad && y < pad + nlf) {
+      for (int t = 0; t < T; ++t) { const cfloat v = k[(((long long)b * T + t) * C + c) * hw + yx]; acc.x += v.x; acc.y += v.y; }
+      acc.x *= invT; acc.y *= invT;
+    }
+    out[(long long)b * per_b + i] = acc;
+  }
+}
+
+__global__ void rss_normalize_kernel(const cfloat* in, cfloat* out, int C, long long hw, long long n_pix) {
+  GRID_STRIDE(i, n_pix) {
+    const long long b = i / hw, p = i % hw;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) { const cfloat v = in[(b * C + c) * hw + p]; acc += v.x * v.x + v.y * v.y; }
+    const float r = sqrtf(acc);
+    for (int c = 0; c < C; ++c) { const cfloat v = in[(b * C + c) * hw + p]; out[(b * C + c) * hw + p] = make_c(v.x / r, v.y / r); }
+  }
+}
+
+__global__ void rss_normalize_bwd_kernel(const cfloat* g, const cfloat* in, cfloat* gin, int C, long long hw, long long n_pix) {
+  GRID_STRIDE(i, n_pix) {
+    const long long b = i / hw, p = i % hw;
+    float ss = 0.f, dot = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const cfloat v = in[(b * C + c) * hw + p], gg = g[(b * C + c) * hw + p];
+      ss += v.x * v.x + v.y * v.y; dot += v.x * gg.x + v.y * gg.y;
+    }
+    const float r = sqrtf(ss), f = dot / (ss * r), ir = 1.f / r;
+    for (int c = 0; c < C; ++c) {
+      const cfloat v = in[(b * C + c) * hw + p], gg = g[(b * C + c) * hw + p];
+      gin[(b * C + c) * hw + p] = make_c(gg.x * ir - v.x * f, gg.y * ir - v.y * f);
+    }
+  }
+}
+
+// ----------------------------- temporal head/tail -------------------------- //
+// one thread per pixel; the t samples of blockDim pixels live in shared memory [t][blockDim]
+__global__ void temporal_kernel(const cfloat* in, const cfloat* mean_in, cfloat* out, cfloat* mean_out, int T, long long hw,
+                                long long n_pix, int xf, int post) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  cfloat* tile = reinterpret_cast<cfloat*>(raw);                 // [T][blockDim]
+  cfloat* tw = tile + (size_t)T * blockDim.x;                    // [T] forward twiddles
+  for (int i = threadIdx.x; i < T; i += blockDim.x) tw[i] = twiddle(i, T);
+  __syncthreads();
+  const int s_in = (T + 1) / 2, s_out = T / 2;
+  const float sc = xf ? rsqrtf((float)T) : 1.f;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pix) return;
+  const long long b = i / hw, p = i % hw;
+  const cfloat* src = in + b * T * hw + p;
+  cfloat* dst = out + b * T * hw + p;
+  cfloat mu = make_c(0.f, 0.f);
+  if (!post) {
+    for (int t = 0; t < T; ++t) { const cfloat v = src[(long long)t * hw]; tile[t * blockDim.x + threadIdx.x] = v; mu.x += v.x; mu.y += v.y; }
+    mu.x /= (float)T; mu.y /= (float)T;
+    mean_out[i] = mu;
+  } else {
+    mu = mean_in[i];
+    for (int t = 0; t < T; ++t) tile[t * blockDim.x + threadIdx.x] = src[(long long)t * hw];
+  }
+  if (!xf) {
+    for (int t = 0; t < T; ++t) {
+      const cfloat v = tile[t * blockDim.x + threadIdx.x];
+      dst[(long long)t * hw] = post ? make_c(v.x + mu.x, v.y + mu.y) : make_c(v.x - mu.x, v.y - mu.y);
+    }
+    return;
+  }
+  for (int kk = 0; kk < T; ++kk) {
+    int kp = kk - s_out; if (kp < 0) kp += T;
+    float ar = 0.f, ai = 0.f;
+    int ph = (s_in * kp) % T;                                    // ((j + s_in) * kp) mod T, j = 0
+    for (int j = 0; j < T; ++j) {
+      cfloat v = tile[j * blockDim.x + threadIdx.x];
+      if (!post) { v.x -= mu.x; v.y -= mu.y; }
+      const cfloat wv = tw[ph];
+      const float wy = post ? -wv.y : wv.y;                      // inverse = conjugate twiddles
+      ar += v.x * wv.x - v.y * wy; ai += v.x * wy + v.y * wv.x;
+      ph += kp; if (ph >= T) ph -= T;
+    }
+    dst[(long long)kk * hw] = post ? make_c(ar * sc + mu.x, ai * sc + mu.y) : make_c(ar * sc, ai * sc);
+  }
+}
+
+// --------------------------------- CG kernels ------------------------------ //
+__global__ void dot_partial_kernel(const float* a, const float* b, float* partial, long long n) {
+  float acc = 0.f;
+  GRID_STRIDE(i, n) acc += a[i] * b[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void dot_final_kernel(const float* partial, float* out, int n) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+__global__ void axpy_ratio_kernel(float* y, const float* x, const float* num, const float* den, float sign, long long n) {
+  const float a = sign * (num[0] / den[0]);
+  GRID_STRIDE(i, n) y[i] = y[i] + a * x[i];
+}
+__global__ void xpay_ratio_kernel(float* p, const float* r, const float* num, const float* den, long long n) {
+  const float bta = num[0] / den[0];
+  GRID_STRIDE(i, n) p[i] = r[i] + bta * p[i];
+}
+__global__ void axpby_kernel(const float* a, const float* b, const float* v, float scale, float* out, long long n) {
+  const float s = v ? v[0] * scale : scale;
+  GRID_STRIDE(i, n) out[i] = a[i] + s * b[i];
+}
+
+}  // namespace
+
+namespace b2s {
+
+int launch_expand_product(const float* image, const float* sens, float* out, int b, int t, int c, int64_t hw, cudaStream_t st) {
+  const long long n = (long long)b * t * c * hw;
+  if (n == 0) return B2S_OK;
+  expand_product_kernel<<<grid_for(n), NT, 0, st>>>((const cfloat*)image, (const cfloat*)sens, (cfloat*)out, t, c, hw, n);
+  return check_launch("expand_product_kernel");
+}
+int launch_kspace_epilogue(float* k, const float* ref, const uint8_t* mask, const float* v, int mode, int64_t n_bt, int c, int h, int w, cudaStream_t st) {
+  const long long n = n_bt * c * h * w;
+  if (n == 0) return B2S_OK;
+  kspace_epilogue_kernel<<<grid_for(n), NT, 0, st>>>((cfloat*)k, (const cfloat*)ref, mask, v, mode, c, h, w, n);
+  return check_launch("kspace_epilogue_kernel");
+}
+int launch_row_weight(const float* k, float* out, const uint8_t* mask, const float* v, int wmode, int64_t n_bt, int c, int h, int w, cudaStream_t st) {
+  const long long n = n_bt * c * h * w;
+  if (n == 0) return B2S_OK;
+  row_weight_kernel<<<grid_for(n), NT, 0, st>>>((const cfloat*)k, (cfloat*)out, mask, v, wmode, c, h, w, n);
+  return check_launch("row_weight_kernel");
+}
+int launch_coil_reduce(const float* y, const float* mult, float* out, int over_frames, int b, int t, int c, int64_t hw, cudaStream_t st) {
+  const long long n_out = (over_frames ? (long long)b * c : (long long)b * t) * hw;
+  if (n_out == 0) return B2S_OK;
+  coil_reduce_kernel<<<grid_for(n_out), NT, 0, st>>>((const cfloat*)y, (const cfloat*)mult, (cfloat*)out, over_frames, t, c, hw, n_out);
+  return check_launch("coil_reduce_kernel");
+}
+
+}  // namespace b2s
+
+extern "C" int b2s_dc_blend(const float* kspace, const float* ref, const uint8_t* mask, const float* v, float* out,
+                            int64_t n_bt, int c, int h, int w, void* stream) {
+  if (!kspace || !ref || !mask || !v || !out || (w & 1)) return fail(w & 1 ? B2S_EUNSUPPORTED : B2S_EINVAL, "b2s_dc_blend: bad argument (w must be even)");
+  const long long n4 = n_bt * c * h * (w / 2);
+  if (n4 == 0) return B2S_OK;
+  dc_blend_kernel<<<grid_for(n4), NT, 0, (cudaStream_t)stream>>>((const float4*)kspace, (const float4*)ref, mask, v, (float4*)out, c, h, w / 2, n4);
+  return check_launch("dc_blend_kernel");
+}
+
+extern "C" int b2s_dc_blend_bwd(const float* g, const float* out, const float* ref, const uint8_t* mask, const float* v,
+                                float* gk, float* gref, float* gv, int64_t n_bt, int c, int h, int w, void* stream) {
+  if (!g || !mask || !v || (gv && (!out || !ref)) || (w & 1)) return fail(B2S_EINVAL, "b2s_dc_blend_bwd: bad argument");
+  const long long n4 = n_bt * c * h * (w / 2);
+  if (n4 == 0) return B2S_OK;
+  dc_blend_bwd_kernel<<<grid_for(n4), NT, 0, (cudaStream_t)stream>>>((const float4*)g, (const float4*)out, (const float4*)ref, mask, v,
+                                                                     (float4*)gk, (float4*)gref, gv, c, h, w / 2, n4);
+  return check_launch("dc_blend_bwd_kernel");
+}
+
+extern "C" int b2s_complex_mul(const float* a, const float* b, float* out, int ndim, const int64_t* shape,
+                               const int64_t* stride_a, const int64_t* stride_b, int conj_b, void* stream) {
+  if (!a || !b || !out || ndim < 0 || ndim > 6 || (ndim && (!shape || !stride_a || !stride_b))) return fail(B2S_EINVAL, "b2s_complex_mul: bad argument");
+  MulDims d; d.nd = ndim; long long n = 1;
+  for (int k = 0; k < 6; ++k) { d.shape[k] = 1; d.sa[k] = 0; d.sb[k] = 0; }
+  for (int k = 0; k < ndim; ++k) { d.shape[k] = shape[k]; d.sa[k] = stride_a[k]; d.sb[k] = stride_b[k]; n *= shape[k]; }
+  if (n == 0) return B2S_OK;
+  complex_mul_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>((const cfloat*)a, (const cfloat*)b, (cfloat*)out, d, conj_b, n);
+  return check_launch("complex_mul_kernel");
+}
+
+extern "C" int b2s_complex_conj(const float* in, float* out, int64_t n, void* stream) {
+  if (!in || !out) return fail(B2S_EINVAL, "b2s_complex_conj: null pointer");
+  if (n == 0) return B2S_OK;
+  complex_conj_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>((const cfloat*)in, (cfloat*)out, n);
+  return check_launch("complex_conj_kernel");
+}
+
+extern "C" int b2s_complex_abs(const float* in, float* out, int64_t n, int squared, void* stream) {
+  if (!in || !out) return fail(B2S_EINVAL, "b2s_complex_abs: null pointer");
+  if (n == 0) return B2S_OK;
+  complex_abs_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>((const cfloat*)in, out, n, squared);
+  return check_launch("complex_abs_kernel");
+}
+
+extern "C" int b2s_rss(const float* in, float* out, int64_t outer, int64_t r, int64_t inner, int is_complex, void* stream) {
+  if (!in || !out) return fail(B2S_EINVAL, "b2s_rss: null pointer");
+  if (outer * inner == 0) return B2S_OK;
+  rss_kernel<<<grid_for(outer * inner), NT, 0, (cudaStream_t)stream>>>(in, out, outer, r, inner, is_complex);
+  return check_launch("rss_kernel");
+}
+
+extern "C" int b2s_acs_mean(const float* kspace, const uint8_t* mask, float* out, int32_t* window_out, int b, int t, int c,
+                            int h, int w, void* stream) {
+  if (!kspace || !mask || !out) return fail(B2S_EINVAL, "b2s_acs_mean: null pointer");
+  const long long per_b = (long long)c * h * w;
+  if (per_b == 0 || b == 0) return B2S_OK;
+  if (t < 1 || b > 65535) return fail(B2S_EUNSUPPORTED, "b2s_acs_mean: need t >= 1 and b <= 65535");
+  const dim3 grid(grid_for(per_b, NT, 148 * 4), (unsigned)b);
+  acs_mean_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>((const cfloat*)kspace, mask, (cfloat*)out, window_out, t, c, h, w);
+  return check_launch("acs_mean_kernel");
+}
+
+extern "C" int b2s_rss_normalize(const float* in, float* out, int b, int c, int64_t hw, void* stream) {
+  if (!in || !out) return fail(B2S_EINVAL, "b2s_rss_normalize: null pointer");
+  const long long n = (long long)b * hw;
+  if (n == 0) return B2S_OK;
+  rss_normalize_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>((const cfloat*)in, (cfloat*)out, c, hw, n);
+  return check_launch("rss_normalize_kernel");
+}
+
+extern "C" int b2s_rss_normalize_bwd(const float* g, const float* in, float* gin, int b, int c, int64_t hw, void* stream) {
+  if (!g || !in || !gin) return fail(B2S_EINVAL, "b2s_rss_normalize_bwd: null pointer");
+  const long long n = (long long)b * hw;
+  if (n == 0) return B2S_OK;
+  rss_normalize_bwd_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>((const cfloat*)g, (const cfloat*)in, (cfloat*)gin, c, hw, n);
+  return check_launch("rss_normalize_bwd_kernel");
+}
+
+static int launch_temporal(const float* in, const float* mean_in, float* out, float* mean_out, int b, int t, int64_t hw,
+                           int xf, int post, void* stream) {
+  if (t < 1 || t > 192) return fail(B2S_EUNSUPPORTED, "temporal length must be in [1, 192]");
+  const long long n_pix = (long long)b * hw;
+  if (n_pix == 0) return B2S_OK;
+  int block = (int)(5632 / t) / 32 * 32;                   // t * block * 8 B + tw <= 48 KB
+  if (block > 128) block = 128;
+  if (block < 32) block = 32;
+  const size_t smem = ((size_t)t * block + t) * sizeof(cfloat);
+  const long long blocks = (n_pix + block - 1) / block;
+  temporal_kernel<<<(unsigned)blocks, block, smem, (cudaStream_t)stream>>>((const cfloat*)in, (const cfloat*)mean_in, (cfloat*)out,
+                                                                           (cfloat*)mean_out, t, hw, n_pix, xf, post);
+  return check_launch("temporal_kernel");
+}
+
+extern "C" int b2s_temporal_pre(const float* image, float* x, float* mean, int b, int t, int64_t hw, int xf, void* stream) {
+  if (!image || !x || !mean) return fail(B2S_EINVAL, "b2s_temporal_pre: null pointer");
+  return launch_temporal(image, nullptr, x, mean, b, t, hw, xf, 0, stream);
+}
+
+extern "C" int b2s_temporal_post(const float* x, const float* mean, float* out, int b, int t, int64_t hw, int xf, void* stream) {
+  if (!x || !mean || !out) return fail(B2S_EINVAL, "b2s_temporal_post: null pointer");
+  return launch_temporal(x, mean, out, nullptr, b, t, hw, xf, 1, stream);
+}
+
+extern "C" int b2s_dot(const float* a, const float* b, float* out, int64_t n, float* scratch, void* stream) {
+  if (!a || !b || !out || !scratch) return fail(B2S_EINVAL, "b2s_dot: null pointer");
+  const unsigned g = grid_for(n, NT, 1024);
+  dot_partial_kernel<<<g, NT, 0, (cudaStream_t)stream>>>(a, b, scratch, n);
+  dot_final_kernel<<<1, NT, 0, (cudaStream_t)stream>>>(scratch, out, (int)g);
+  return check_launch("dot kernels");
+}
+
+extern "C" int b2s_axpy_ratio(float* y, const float* x, const float* num, const float* den, float sign, int64_t n, void* stream) {
+  if (!y || !x || !num || !den) return fail(B2S_EINVAL, "b2s_axpy_ratio: null pointer");
+  if (n == 0) return B2S_OK;
+  axpy_ratio_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(y, x, num, den, sign, n);
+  return check_launch("axpy_ratio_kernel");
+}
+
+extern "C" int b2s_xpay_ratio(float* p, const float* r, const float* num, const float* den, int64_t n, void* stream) {
+  if (!p || !r || !num || !den) return fail(B2S_EINVAL, "b2s_xpay_ratio: null pointer");
+  if (n == 0) return B2S_OK;
+  xpay_ratio_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(p, r, num, den, n);
+  return check_launch("xpay_ratio_kernel");
+}
+
+extern "C" int b2s_axpby(const float* a, const float* b, const float* v, float scale, float* out, int64_t n, void* stream) {
+  if (!a || !b || !out) return fail(B2S_EINVAL, "b2s_axpby: null pointer");
+  if (n == 0) return B2S_OK;
+  axpby_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(a, b, v, scale, out, n);
+  return check_launch("axpby_kernel");
+}

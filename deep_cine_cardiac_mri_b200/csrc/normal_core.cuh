@@ -1,0 +1,181 @@
+// CineNet normal operator  H x = A^H M A x + v x  (models/cinenet.py:121-133,
+// recurrent_cinenet.py:74-86) with the k-space kept on chip.
+//
+// The mask selects k-space ROWS only (data/subsample.py:146-151), so it commutes
+// with the transform along w and  F^H M F = (F_h^H M F_h) (x) I_w :
+//
+//     H x = sum_c conj(S_c) . [ F_h^H M F_h (S_c . x) ]  +  v x .
+//
+// No FFT along w is needed at all, every image column is independent, and the
+// c * K bytes of intermediate k-space of the reference never exist.  One CTA
+// owns XC adjacent columns of one frame, loops over the coils and keeps the
+// coil sum in registers (deterministic, no atomics).
+//
+// Length-H transform, H = 8*G (G = 25):  forward  = radix-G over rows {m + 8 i}
+// (thread (m, x) owns exactly those rows, the same rows its accumulator holds),
+// twiddle, radix-8 over m giving bins k = g + G*k2;  the mask is applied there
+// and the inverse starts immediately in the same registers with the radix-8 over
+// {g + G*j}, twiddle, then radix-G giving rows m + 8*k.  Two shared-memory
+// exchanges per coil.  Centring: input/output signs (-1)^y = (-1)^m.
+#pragma once
+#include "fft2_core.cuh"
+
+namespace b2s {
+
+template <int H_, int XC_> struct NormalPlan {
+  static constexpr int H = H_, G = H_ / 8, XC = XC_;
+  static constexpr int NT = 8 * XC_;
+  static constexpr int E_ELEMS = H_ * XC_;           // exchange buffer [g][m][x]
+  static constexpr int TW_OFF = E_ELEMS;             // w_H^n, n in [0,H)
+  static constexpr int SMEM_ELEMS = TW_OFF + H_;
+  static constexpr int SMEM_BYTES = SMEM_ELEMS * 8 + H_;   // + mask row (uint8)
+  static constexpr int TASKS2 = G * XC_;
+  static_assert(H_ % 8 == 0, "H must be a multiple of 8");
+};
+
+struct NormalArgs {
+  const cfloat* x; const cfloat* sens; const uint8_t* mask; const float* vptr; cfloat* out;
+  int T, C, W;
+};
+
+// step 1: p = S_c x, radix-G over this thread's rows, twiddle, store E[g][m][xl]
+template <class P>
+B2S_HD void normal_step1(const NormalArgs& a, cfloat* smem, long long bt, int c, int x0, int tid) {
+  constexpr int G = P::G, XC = P::XC;
+  const int m = tid / XC, xl = tid - m * XC, x = x0 + xl;
+  const long long b = bt / a.T;
+  const long long hw = (long long)P::H * a.W;
+  const cfloat* xp = a.x + bt * hw + x;
+  const cfloat* sp = a.sens + (b * a.C + c) * hw + x;
+  float re[G], im[G];
+  const float sg = (m & 1) ? -1.f : 1.f;
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const long long row = (long long)(m + 8 * i) * a.W;
+    const cfloat xv = xp[row], sv = sp[row];
+    re[i] = (xv.x * sv.x - xv.y * sv.y) * sg;
+    im[i] = (xv.x * sv.y + xv.y * sv.x) * sg;
+  }
+  Dft<G>::run(re, im);
+  const cfloat* tw = smem + P::TW_OFF;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const cfloat w = tw[m * g];                       // m*g <= 7*(G-1) < H
+    smem[(g * 8 + m) * XC + xl] = make_c(re[g] * w.x - im[g] * w.y, re[g] * w.y + im[g] * w.x);
+  }
+}
+
+// step 2: radix-8 over m -> bins g + G*k2, mask, inverse radix-8 over {g + G*j}, twiddle, in place
+template <class P>
+B2S_HD void normal_step2(cfloat* smem, const uint8_t* mrow, int task) {
+  constexpr int G = P::G, XC = P::XC;
+  const int g = task / XC, xl = task - g * XC;
+  float re[8], im[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const cfloat v = smem[(g * 8 + j) * XC + xl]; re[j] = v.x; im[j] = v.y; }
+  dft8(re, im);
+#pragma unroll
+  for (int k2 = 0; k2 < 8; ++k2) {
+    const float mk = mrow[g + G * k2] ? 1.f : 0.f;
+    re[k2] *= mk; im[k2] *= mk;
+  }
+  dft8(im, re);                                        // inverse = forward on swapped data
+  const cfloat* tw = smem + P::TW_OFF;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const cfloat w = tw[m * g];
+    // still in the swapped domain: value = (im, re)
+    smem[(g * 8 + m) * XC + xl] = make_c(im[m] * w.x - re[m] * w.y, im[m] * w.y + re[m] * w.x);
+  }
+}
+
+// step 3: radix-G over g -> rows m + 8k (swapped domain), un-swap, sign, conj(S_c), accumulate
+template <class P>
+B2S_HD void normal_step3(const NormalArgs& a, const cfloat* smem, long long bt, int c, int x0, int tid,
+                         float (&accr)[P::G], float (&acci)[P::G], float scale) {
+  constexpr int G = P::G, XC = P::XC;
+  const int m = tid / XC, xl = tid - m * XC, x = x0 + xl;
+  const long long b = bt / a.T;
+  const long long hw = (long long)P::H * a.W;
+  const cfloat* sp = a.sens + (b * a.C + c) * hw + x;
+  float re[G], im[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) { const cfloat v = smem[(g * 8 + m) * XC + xl]; re[g] = v.x; im[g] = v.y; }
+  Dft<G>::run(re, im);
+  const float s = (m & 1) ? -scale : scale;
+#pragma unroll
+  for (int k = 0; k < G; ++k) {
+    const cfloat sv = sp[(long long)(m + 8 * k) * a.W];
+    const float yr = im[k] * s, yi = re[k] * s;        // un-swap
+    accr[k] += yr * sv.x + yi * sv.y;
+    acci[k] += yi * sv.x - yr * sv.y;
+  }
+}
+
+template <class P>
+B2S_HD void normal_finish(const NormalArgs& a, long long bt, int x0, int tid, const float (&accr)[P::G],
+                          const float (&acci)[P::G], float v) {
+  constexpr int G = P::G, XC = P::XC;
+  const int m = tid / XC, xl = tid - m * XC, x = x0 + xl;
+  const long long hw = (long long)P::H * a.W;
+#pragma unroll
+  for (int k = 0; k < G; ++k) {
+    const long long off = bt * hw + (long long)(m + 8 * k) * a.W + x;
+    const cfloat xv = a.x[off];
+    a.out[off] = make_c(accr[k] + v * xv.x, acci[k] + v * xv.y);
+  }
+}
+
+#if defined(__CUDACC__)
+template <class P>
+__global__ void __launch_bounds__(P::NT, 3) normal_op_kernel(const NormalArgs a) {
+  extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
+  cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);
+  uint8_t* mrow = reinterpret_cast<uint8_t*>(smem + P::SMEM_ELEMS);
+  const int tid = threadIdx.x;
+  const int chunks = a.W / P::XC;
+  const long long bt = blockIdx.x / chunks;
+  const int x0 = (blockIdx.x % chunks) * P::XC;
+  for (int n = tid; n < P::H; n += P::NT) { smem[P::TW_OFF + n] = twiddle(n, P::H); mrow[n] = a.mask[bt * P::H + n]; }
+  float accr[P::G], acci[P::G];
+#pragma unroll
+  for (int k = 0; k < P::G; ++k) { accr[k] = 0.f; acci[k] = 0.f; }
+  const float scale = 1.f / (float)P::H;              // ortho forward * ortho inverse along h
+  __syncthreads();
+#pragma unroll 1
+  for (int c = 0; c < a.C; ++c) {
+    normal_step1<P>(a, smem, bt, c, x0, tid);
+    __syncthreads();
+    for (int task = tid; task < P::TASKS2; task += P::NT) normal_step2<P>(smem, mrow, task);
+    __syncthreads();
+    normal_step3<P>(a, smem, bt, c, x0, tid, accr, acci, scale);
+    __syncthreads();
+  }
+  normal_finish<P>(a, bt, x0, tid, accr, acci, *a.vptr);
+}
+#endif
+
+template <class P>
+void normal_op_emulate(const NormalArgs& a, long long n_bt) {
+  cfloat* smem = new cfloat[P::SMEM_ELEMS];
+  uint8_t* mrow = new uint8_t[P::H];
+  float (*accr)[P::G] = new float[P::NT][P::G];
+  float (*acci)[P::G] = new float[P::NT][P::G];
+  const int chunks = a.W / P::XC;
+  for (long long blk = 0; blk < n_bt * chunks; ++blk) {
+    const long long bt = blk / chunks;
+    const int x0 = (int)(blk % chunks) * P::XC;
+    for (int n = 0; n < P::H; ++n) { smem[P::TW_OFF + n] = twiddle(n, P::H); mrow[n] = a.mask[bt * P::H + n]; }
+    for (int tid = 0; tid < P::NT; ++tid) for (int k = 0; k < P::G; ++k) { accr[tid][k] = 0.f; acci[tid][k] = 0.f; }
+    for (int c = 0; c < a.C; ++c) {
+      for (int tid = 0; tid < P::NT; ++tid) normal_step1<P>(a, smem, bt, c, x0, tid);
+      for (int tid = 0; tid < P::NT; ++tid)
+        for (int task = tid; task < P::TASKS2; task += P::NT) normal_step2<P>(smem, mrow, task);
+      for (int tid = 0; tid < P::NT; ++tid) normal_step3<P>(a, smem, bt, c, x0, tid, accr[tid], acci[tid], 1.f / (float)P::H);
+    }
+    for (int tid = 0; tid < P::NT; ++tid) normal_finish<P>(a, bt, x0, tid, accr[tid], acci[tid], *a.vptr);
+  }
+  delete[] smem; delete[] mrow; delete[] accr; delete[] acci;
+}
+
+}  // namespace b2s

@@ -1,0 +1,627 @@
+"""PyTorch custom operators over the C ABI (include/b200sense.h).
+
+Layering:  `raw_*`  = one ABI call on the current CUDA stream, no autograd;
+`*Fn` autograd Functions use the adjoint kernels as the backward
+(SURVEY.md section 10); the module-level functions at the bottom are what
+`functional.py` / `blocks.py` call.  Tensors must be float32 CUDA tensors —
+anything else raises (there is no CPU or cuFFT fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+NORM = {None: 0, "backward": 0, "ortho": 1, "forward": 2}
+_ADJ_NORM = {0: 2, 1: 1, 2: 0}          # adjoint of a transform with norm n is the inverse with this norm
+EXPAND_PLAIN, EXPAND_MASK, EXPAND_DC, EXPAND_RESIDUAL = 0, 1, 2, 3
+REDUCE_PLAIN, REDUCE_MASK, REDUCE_DCGRAD = 0, 1, 2
+
+
+# --------------------------------------------------------------------------- #
+# plumbing
+# --------------------------------------------------------------------------- #
+def _norm(norm) -> int:
+    try:
+        return NORM[norm]
+    except KeyError:
+        raise RuntimeError(f"Invalid normalization mode: {norm!r}") from None
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts) -> None:
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("b200sense operators run on CUDA tensors only "
+                               "(there is no CPU fallback); got a tensor on " + str(t.device))
+        if t.dtype != torch.float32 and t.dtype != torch.uint8:
+            raise TypeError(f"b200sense operators are float32 (got {t.dtype})")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """contiguous float32 (no copy when already so)"""
+    if t.dtype != torch.float32:
+        raise TypeError(f"b200sense operators are float32 (got {t.dtype})")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _mask_u8(mask: torch.Tensor, b: int, t: int, h: int) -> torch.Tensor:
+    """reference mask (b,t,1,h,1,1) (uint8 / float / bool) -> contiguous uint8 (b,t,h)."""
+    m = mask
+    if m.dtype != torch.uint8:
+        m = (m != 0).to(torch.uint8)
+    if m.numel() != b * t * h:
+        m = m.expand(b, t, 1, h, 1, 1) if m.dim() == 6 else m.expand(b, t, h)
+    return m.reshape(b, t, h).contiguous()
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _vdev(v, device) -> torch.Tensor:
+    """softplus(lambda) as a 1-element float32 device tensor (no host sync)."""
+    if isinstance(v, torch.Tensor):
+        return v.detach().reshape(-1)[:1].to(device=device, dtype=torch.float32).contiguous()
+    return torch.full((1,), float(v), dtype=torch.float32, device=device)
+
+
+_scratch = {}
+
+
+def _scratch_for(b, t, c, h, w, device):
+    n = _lib.lib().b2s_scratch_bytes(b, t, c, h, w)
+    if n == 0:
+        return None, 0
+    key = (device.index, "s")
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(n, dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf, n
+
+
+# --------------------------------------------------------------------------- #
+# raw calls
+# --------------------------------------------------------------------------- #
+def raw_fft2c(x: torch.Tensor, inverse: bool, norm: int) -> torch.Tensor:
+    _need_cuda(x)
+    x = _f32c(x)
+    h, w = x.shape[-3], x.shape[-2]
+    out = torch.empty_like(x)
+    n = x.numel() // (2 * h * w) if h * w else 0
+    _lib.check(_lib.lib().b2s_fft2c(_p(x), _p(out), n, h, w, int(inverse), norm, _stream()), "fft2c")
+    return out
+
+
+def raw_fft1c_layout(x: torch.Tensor, outer: int, n: int, inner: int, inverse: bool, norm: int,
+                     shift_in: int, shift_out: int, out: torch.Tensor) -> None:
+    _lib.check(_lib.lib().b2s_fft1c(_p(x), _p(out), outer, n, inner, int(inverse), norm, shift_in, shift_out,
+                                    _stream()), "fft1c")
+
+
+def raw_sens_expand(image, sens, mode=EXPAND_PLAIN, ref=None, mask_u8=None, v=None, norm=1):
+    """image (b,t,h,w,2), sens (b,c,h,w,2) -> (b,t,c,h,w,2)."""
+    _need_cuda(image, sens, ref, mask_u8, v)
+    b, t, h, w, _ = image.shape
+    c = sens.shape[1]
+    out = torch.empty((b, t, c, h, w, 2), dtype=torch.float32, device=image.device)
+    sc, nsc = _scratch_for(b, t, c, h, w, image.device)
+    _lib.check(_lib.lib().b2s_sens_expand(_p(image), _p(sens), _p(out), _p(ref), _p(mask_u8), _p(v), mode,
+                                          b, t, c, h, w, norm, _p(sc), nsc, _stream()), "sens_expand")
+    return out
+
+
+def raw_sens_reduce(kspace, mult, wmode=REDUCE_PLAIN, over_frames=False, mask_u8=None, v=None, norm=1):
+    """kspace (b,t,c,h,w,2); mult = sens (b,c,h,w,2) -> (b,t,h,w,2), or (over_frames) mult = image
+    (b,t,h,w,2) -> (b,c,h,w,2)."""
+    _need_cuda(kspace, mult, mask_u8, v)
+    b, t, c, h, w, _ = kspace.shape
+    shape = (b, c, h, w, 2) if over_frames else (b, t, h, w, 2)
+    out = torch.empty(shape, dtype=torch.float32, device=kspace.device)
+    sc, nsc = _scratch_for(b, t, c, h, w, kspace.device)
+    _lib.check(_lib.lib().b2s_sens_reduce(_p(kspace), _p(mult), _p(out), _p(mask_u8), _p(v), wmode,
+                                          int(over_frames), b, t, c, h, w, norm, _p(sc), nsc, _stream()),
+               "sens_reduce")
+    return out
+
+
+def raw_dc_blend(k, ref, mask_u8, v):
+    _need_cuda(k, ref, mask_u8, v)
+    b, t, c, h, w, _ = k.shape
+    out = torch.empty_like(k)
+    _lib.check(_lib.lib().b2s_dc_blend(_p(k), _p(ref), _p(mask_u8), _p(v), _p(out), b * t, c, h, w, _stream()),
+               "dc_blend")
+    return out
+
+
+def raw_dc_blend_bwd(g, out, ref, mask_u8, v, want_gk, want_gref, want_gv):
+    b, t, c, h, w, _ = g.shape
+    gk = torch.empty_like(g) if want_gk else None
+    gref = torch.empty_like(g) if want_gref else None
+    gv = torch.zeros(1, dtype=torch.float32, device=g.device) if want_gv else None
+    _lib.check(_lib.lib().b2s_dc_blend_bwd(_p(g), _p(out), _p(ref), _p(mask_u8), _p(v), _p(gk), _p(gref), _p(gv),
+                                           b * t, c, h, w, _stream()), "dc_blend_bwd")
+    return gk, gref, gv
+
+
+def raw_normal_op(x, sens, mask_u8, v):
+    """x (b,t,h,w,2) -> A^H M A x + v x (on-chip kernel; h == 200)."""
+    _need_cuda(x, sens, mask_u8, v)
+    b, t, h, w, _ = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().b2s_normal_op(_p(x), _p(sens), _p(mask_u8), _p(v), _p(out), b, t, sens.shape[1], h, w,
+                                        _stream()), "normal_op")
+    return out
+
+
+def normal_op_supported(h: int, w: int) -> bool:
+    return h == 200 and w % 20 == 0
+
+
+def raw_temporal_pre(image, xf: bool):
+    """image (b,t,h,w,2) -> (x, mean (b,h,w,2))"""
+    _need_cuda(image)
+    b, t = image.shape[:2]
+    hw = image[0, 0].numel() // 2
+    x = torch.empty_like(image)
+    mean = torch.empty(image.shape[:1] + image.shape[2:], dtype=torch.float32, device=image.device)
+    _lib.check(_lib.lib().b2s_temporal_pre(_p(image), _p(x), _p(mean), b, t, hw, int(xf), _stream()), "temporal_pre")
+    return x, mean
+
+
+def raw_temporal_post(x, mean, xf: bool):
+    _need_cuda(x, mean)
+    b, t = x.shape[:2]
+    hw = mean[0].numel() // 2
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().b2s_temporal_post(_p(x), _p(mean), _p(out), b, t, hw, int(xf), _stream()), "temporal_post")
+    return out
+
+
+def raw_axpby(a, b, v=None, scale=1.0):
+    out = torch.empty_like(a)
+    _lib.check(_lib.lib().b2s_axpby(_p(a), _p(b), _p(v), float(scale), _p(out), a.numel(), _stream()), "axpby")
+    return out
+
+
+def raw_dot(a, b, out=None, scratch=None):
+    out = torch.empty(1, dtype=torch.float32, device=a.device) if out is None else out
+    scratch = torch.empty(1024, dtype=torch.float32, device=a.device) if scratch is None else scratch
+    _lib.check(_lib.lib().b2s_dot(_p(a), _p(b), _p(out), a.numel(), _p(scratch), _stream()), "dot")
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# autograd Functions
+# --------------------------------------------------------------------------- #
+class FFT2cFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inverse, norm):
+        ctx.inverse, ctx.norm = inverse, norm
+        return raw_fft2c(x, inverse, norm)
+
+    @staticmethod
+    def backward(ctx, g):
+        return FFT2cFn.apply(g, not ctx.inverse, _ADJ_NORM[ctx.norm]), None, None
+
+
+def _dense_layout(x: torch.Tensor):
+    """(outer, n, inner) of the memory layout of x (..., n, 2) w.r.t. dim -2, or None if x is not a
+    dense permutation with the complex pair innermost in memory."""
+    if x.stride(-1) != 1 or x.numel() == 0:
+        return None
+    dims = sorted(range(x.dim() - 1), key=lambda d: (-x.stride(d), d))
+    expect = 2
+    for d in reversed(dims):
+        if x.shape[d] != 1 and x.stride(d) != expect:
+            return None
+        expect *= x.shape[d]
+    pos = dims.index(x.dim() - 2)
+    outer = 1
+    for d in dims[:pos]:
+        outer *= x.shape[d]
+    inner = 1
+    for d in dims[pos + 1:]:
+        inner *= x.shape[d]
+    return outer, x.shape[-2], inner
+
+
+class FFT1cFn(torch.autograd.Function):
+    """Centred 1-D transform over dim -2 of (..., n, 2); handles the reference's permuted views
+    (varnet.py:211-213) in place, without materialising the permutation."""
+
+    @staticmethod
+    def forward(ctx, x, inverse, norm, shift_in, shift_out):
+        _need_cuda(x)
+        if x.dtype != torch.float32:
+            raise TypeError(f"b200sense operators are float32 (got {x.dtype})")
+        lay = _dense_layout(x)
+        if lay is None:
+            x = x.contiguous()
+            lay = (x.numel() // (2 * x.shape[-2]), x.shape[-2], 1)
+        out = torch.empty_like(x)               # preserve_format keeps the dense permuted strides
+        if out.stride() != x.stride():
+            x = x.contiguous()
+            out = torch.empty_like(x)
+            lay = (x.numel() // (2 * x.shape[-2]), x.shape[-2], 1)
+        ctx.args = (inverse, norm, shift_in, shift_out)
+        if x.numel():
+            raw_fft1c_layout(x, lay[0], lay[1], lay[2], inverse, norm, shift_in, shift_out, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        inverse, norm, s_in, s_out = ctx.args
+        return FFT1cFn.apply(g, not inverse, _ADJ_NORM[norm], -s_out, -s_in), None, None, None, None
+
+
+class SensExpandFn(torch.autograd.Function):
+    """k = Epi(F(S x)); backward: gx = A^H(w g), gS = sum_t conj(x) F^H(w g), gref, gv."""
+
+    @staticmethod
+    def forward(ctx, image, sens, ref, mask_u8, v, mode, norm):
+        image, sens = _f32c(image), _f32c(sens)
+        ref = _f32c(ref) if ref is not None else None
+        vd = v.detach() if v is not None else None
+        out = raw_sens_expand(image, sens, mode, ref, mask_u8, vd, norm)
+        ctx.mode, ctx.norm = mode, norm
+        ctx.save_for_backward(image, sens, ref, mask_u8, vd, out if mode == EXPAND_DC else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        image, sens, ref, mask_u8, v, out = ctx.saved_tensors
+        g = _f32c(g)
+        wmode = {EXPAND_PLAIN: REDUCE_PLAIN, EXPAND_MASK: REDUCE_MASK, EXPAND_DC: REDUCE_DCGRAD,
+                 EXPAND_RESIDUAL: REDUCE_MASK}[ctx.mode]
+        adj = _ADJ_NORM[ctx.norm]
+        need = ctx.needs_input_grad
+        gx = raw_sens_reduce(g, sens, wmode, False, mask_u8, v, adj) if need[0] else None
+        gs = raw_sens_reduce(g, image, wmode, True, mask_u8, v, adj) if need[1] else None
+        gref = gv = None
+        if ctx.mode == EXPAND_DC and (need[2] or need[4]):
+            _, gref, gv = raw_dc_blend_bwd(g, out, ref, mask_u8, v, False, need[2], need[4])
+        elif ctx.mode == EXPAND_RESIDUAL and need[2]:
+            gref = -g
+        return gx, gs, gref, None, gv, None, None
+
+
+class SensReduceFn(torch.autograd.Function):
+    """x = sum_c conj(S) F^H(w k); backward: gk = w F(S g), gS = sum_t conj(g) F^H(w k)."""
+
+    @staticmethod
+    def forward(ctx, kspace, sens, mask_u8, wmode, norm):
+        kspace, sens = _f32c(kspace), _f32c(sens)
+        ctx.wmode, ctx.norm = wmode, norm
+        ctx.save_for_backward(kspace, sens, mask_u8)
+        return raw_sens_reduce(kspace, sens, wmode, False, mask_u8, None, norm)
+
+    @staticmethod
+    def backward(ctx, g):
+        kspace, sens, mask_u8 = ctx.saved_tensors
+        g = _f32c(g)
+        need = ctx.needs_input_grad
+        adj = _ADJ_NORM[ctx.norm]
+        gk = gs = None
+        if need[0]:
+            gk = SensExpandFn.apply(g, sens, None, mask_u8, None,
+                                    EXPAND_MASK if ctx.wmode == REDUCE_MASK else EXPAND_PLAIN, adj)
+        if need[1]:
+            gs = raw_sens_reduce(kspace, g, ctx.wmode, True, mask_u8, None, ctx.norm)
+        return gk, gs, None, None, None
+
+
+class DCBlendFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, k, ref, mask_u8, v):
+        k, ref = _f32c(k), _f32c(ref)
+        vd = v.detach()
+        out = raw_dc_blend(k, ref, mask_u8, vd)
+        ctx.save_for_backward(out, ref, mask_u8, vd)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, ref, mask_u8, v = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        gk, gref, gv = raw_dc_blend_bwd(_f32c(g), out, ref, mask_u8, v, need[0], need[1], need[3])
+        return gk, gref, None, gv
+
+
+class NormalOpFn(torch.autograd.Function):
+    """H = A^H M A + v is self-adjoint: gx = H g, gv = <g, x>."""
+
+    @staticmethod
+    def forward(ctx, x, sens, mask_u8, v):
+        x, sens = _f32c(x), _f32c(sens)
+        vd = v.detach()
+        ctx.save_for_backward(x, sens, mask_u8, vd)
+        return raw_normal_op(x, sens, mask_u8, vd)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, sens, mask_u8, v = ctx.saved_tensors
+        g = _f32c(g)
+        need = ctx.needs_input_grad
+        gx = NormalOpFn.apply(g, sens, mask_u8, v) if need[0] else None
+        gv = raw_dot(g, x) if need[3] else None
+        return gx, None, None, gv
+
+
+class TemporalPreFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, xf):
+        ctx.xf = xf
+        x, mean = raw_temporal_pre(_f32c(image), xf)
+        return x, mean
+
+    @staticmethod
+    def backward(ctx, gx, gmean):
+        # x = F_t (I - 11^T/T) image ; mean = 11^T/T image  (both linear)
+        t = gx.shape[1]
+        gx = _f32c(gx)
+        zero_mean = torch.zeros(gx.shape[:1] + gx.shape[2:], dtype=torch.float32, device=gx.device)
+        tmp = raw_temporal_post(gx, zero_mean, ctx.xf) if ctx.xf else gx        # adjoint of fft1c = ifft1c
+        gi, _ = raw_temporal_pre(tmp, False)                                    # subtract temporal mean
+        if gmean is not None:
+            gi = gi + (gmean / t).unsqueeze(1)
+        return gi, None
+
+
+class TemporalPostFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mean, xf):
+        ctx.xf = xf
+        return raw_temporal_post(_f32c(x), _f32c(mean), xf)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        t = g.shape[1]
+        need = ctx.needs_input_grad
+        gx = gm = None
+        if need[0] or need[1]:
+            centred, mean_g = raw_temporal_pre(g, False)
+            if need[1]:
+                gm = mean_g * t
+            if need[0]:
+                if ctx.xf:
+                    # adjoint of ifft1c = fft1c, applied to g itself (not mean-subtracted)
+                    b = g.shape[0]
+                    hw = mean_g[0].numel() // 2
+                    gx = torch.empty_like(g)
+                    raw_fft1c_layout(g, b, t, hw, False, 1, (t + 1) // 2, t // 2, gx)
+                else:
+                    gx = g
+        return gx, gm, None
+
+
+class RssNormalizeFn(torch.autograd.Function):
+    """x / rss_complex(x, coil dim 1) on (b,c,h,w,2) — varnet.py:58-59."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = _f32c(x)
+        b, c = x.shape[:2]
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().b2s_rss_normalize(_p(x), _p(out), b, c, x[0, 0].numel() // 2, _stream()), "rss_normalize")
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _f32c(g)
+        b, c = x.shape[:2]
+        gin = torch.empty_like(x)
+        _lib.check(_lib.lib().b2s_rss_normalize_bwd(_p(g), _p(x), _p(gin), b, c, x[0, 0].numel() // 2, _stream()),
+                   "rss_normalize_bwd")
+        return gin
+
+
+class AcsMeanFn(torch.autograd.Function):
+    """mask_center(mean_t(k), ACS window) — varnet.py:64-71 (device-side window, no host sync)."""
+
+    @staticmethod
+    def forward(ctx, kspace, mask_u8):
+        _need_cuda(kspace, mask_u8)
+        kspace = _f32c(kspace)
+        b, t, c, h, w, _ = kspace.shape
+        out = torch.empty((b, c, h, w, 2), dtype=torch.float32, device=kspace.device)
+        win = torch.empty((b, 2), dtype=torch.int32, device=kspace.device)
+        _lib.check(_lib.lib().b2s_acs_mean(_p(kspace), _p(mask_u8), _p(out), _p(win), b, t, c, h, w, _stream()), "acs_mean")
+        ctx.save_for_backward(win)
+        ctx.t = t
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (win,) = ctx.saved_tensors
+        b, c, h, w, _ = g.shape
+        rows = torch.arange(h, device=g.device).view(1, h)
+        keep = ((rows >= win[:, :1]) & (rows < win[:, :1] + win[:, 1:2])).to(g.dtype)      # (b,h)
+        gk = (g * keep.view(b, 1, h, 1, 1) / ctx.t).unsqueeze(1).expand(b, ctx.t, c, h, w, 2)
+        return gk.contiguous(), None
+
+
+# --------------------------------------------------------------------------- #
+# element-wise ops of utils/math.py / coil_combine.py (forward kernels; torch autograd via formulas)
+# --------------------------------------------------------------------------- #
+def _bcast_strides(t: torch.Tensor, shape):
+    te = t.expand(*shape, 2)
+    if te.stride(-1) != 1 or any(s % 2 for s in te.stride()[:-1]):
+        te = t.contiguous().expand(*shape, 2)
+    return te, [s // 2 for s in te.stride()[:-1]]
+
+
+def raw_complex_mul(x, y, conj_y=False):
+    _need_cuda(x, y)
+    if x.dtype != torch.float32 or y.dtype != torch.float32:
+        raise TypeError("b200sense operators are float32")
+    shape = torch.broadcast_shapes(x.shape[:-1], y.shape[:-1])
+    out = torch.empty(*shape, 2, dtype=torch.float32, device=x.device)
+    # collapse to <= 6 dims by merging is not attempted; the reference never exceeds 5 leading dims
+    if len(shape) > 6:
+        raise ValueError("complex_mul: more than 6 leading dimensions")
+    xe, sx = _bcast_strides(x, shape)
+    ye, sy = _bcast_strides(y, shape)
+    n = len(shape)
+    arr = C.c_int64 * max(n, 1)
+    _lib.check(_lib.lib().b2s_complex_mul(_p(xe), _p(ye), _p(out), n, arr(*shape), arr(*sx), arr(*sy), int(conj_y),
+                                          _stream()), "complex_mul")
+    return out
+
+
+def _sum_to(g, shape):
+    if tuple(g.shape) == tuple(shape):
+        return g
+    lead = g.dim() - len(shape)
+    if lead:
+        g = g.sum(dim=tuple(range(lead)))
+    dims = tuple(i for i, (a, b) in enumerate(zip(g.shape, shape)) if a != b)
+    return g.sum(dim=dims, keepdim=True) if dims else g
+
+
+class ComplexMulFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        ctx.save_for_backward(x, y)
+        return raw_complex_mul(x, y)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        g = _f32c(g)
+        gx = _sum_to(raw_complex_mul(g, y, conj_y=True), x.shape) if ctx.needs_input_grad[0] else None
+        gy = _sum_to(raw_complex_mul(g, x, conj_y=True), y.shape) if ctx.needs_input_grad[1] else None
+        return gx, gy
+
+
+class ComplexConjFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = _f32c(x)
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().b2s_complex_conj(_p(x), _p(out), x.numel() // 2, _stream()), "complex_conj")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return ComplexConjFn.apply(g)
+
+
+class ComplexAbsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, squared):
+        _need_cuda(x)
+        x = _f32c(x)
+        out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().b2s_complex_abs(_p(x), _p(out), x.numel() // 2, int(squared), _stream()), "complex_abs")
+        ctx.squared = squared
+        ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out = ctx.saved_tensors
+        if ctx.squared:
+            return 2 * x * g.unsqueeze(-1), None
+        return x * (g / out).unsqueeze(-1), None
+
+
+class RssFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dim, is_complex):
+        _need_cuda(x)
+        x = _f32c(x)
+        nd = x.dim() - (1 if is_complex else 0)
+        d = dim % x.dim()
+        if is_complex and d == x.dim() - 1:
+            raise ValueError("rss_complex: dim must not be the complex dimension")
+        outer = 1
+        for s in x.shape[:d]:
+            outer *= s
+        inner = 1
+        for s in x.shape[d + 1:nd]:
+            inner *= s
+        oshape = x.shape[:d] + x.shape[d + 1:nd]
+        out = torch.empty(oshape, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().b2s_rss(_p(x), _p(out), outer, x.shape[d], inner, int(is_complex), _stream()), "rss")
+        ctx.d, ctx.is_complex = d, is_complex
+        ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out = ctx.saved_tensors
+        r = (g / out).unsqueeze(ctx.d)
+        if ctx.is_complex:
+            r = r.unsqueeze(-1)
+        return x * r, None, None
+
+
+# --------------------------------------------------------------------------- #
+# public entry points used by functional.py / blocks.py
+# --------------------------------------------------------------------------- #
+def fft2c(x, norm="ortho", inverse=False):
+    return FFT2cFn.apply(x, inverse, _norm(norm))
+
+
+def fft1c(x, norm="ortho", inverse=False, shift_in=None, shift_out=None):
+    n = x.shape[-2]
+    s_in = (n + 1) // 2 if shift_in is None else shift_in
+    s_out = n // 2 if shift_out is None else shift_out
+    return FFT1cFn.apply(x, inverse, _norm(norm), s_in, s_out)
+
+
+def sens_expand(image, sens, mode=EXPAND_PLAIN, ref=None, mask=None, v=None, norm="ortho"):
+    """image (b,t,h,w,2) or (b,t,1,h,w,2); sens (b,c,h,w,2) or (b,1,c,h,w,2) -> (b,t,c,h,w,2)."""
+    if image.dim() == 6:
+        image = image.squeeze(2)
+    if sens.dim() == 6:
+        sens = sens.squeeze(1)
+    b, t, h, w, _ = image.shape
+    m8 = _mask_u8(mask, b, t, h) if mask is not None else None
+    vd = _vdev(v, image.device) if (v is not None and not isinstance(v, torch.Tensor)) else v
+    if isinstance(vd, torch.Tensor) and vd.numel() != 1:
+        raise ValueError("v must be a scalar")
+    if isinstance(vd, torch.Tensor):
+        vd = vd.reshape(1).to(device=image.device, dtype=torch.float32)
+    return SensExpandFn.apply(image, sens, ref, m8, vd, mode, _norm(norm))
+
+
+def sens_reduce(kspace, sens, mask=None, norm="ortho"):
+    """kspace (b,t,c,h,w,2), sens (b,c,h,w,2)|(b,1,c,h,w,2) -> (b,t,h,w,2)."""
+    if sens.dim() == 6:
+        sens = sens.squeeze(1)
+    b, t, c, h, w, _ = kspace.shape
+    m8 = _mask_u8(mask, b, t, h) if mask is not None else None
+    return SensReduceFn.apply(kspace, sens, m8, REDUCE_MASK if mask is not None else REDUCE_PLAIN, _norm(norm))
+
+
+def dc_blend(k, ref, mask, v):
+    b, t, c, h, w, _ = k.shape
+    vd = v.reshape(1).to(device=k.device, dtype=torch.float32) if isinstance(v, torch.Tensor) else _vdev(v, k.device)
+    return DCBlendFn.apply(k, ref, _mask_u8(mask, b, t, h), vd)
+
+
+def normal_op(x, sens, mask, v):
+    """x (b,t,h,w,2) -> A^H M A x + v x."""
+    if sens.dim() == 6:
+        sens = sens.squeeze(1)
+    b, t, h, w, _ = x.shape
+    vd = v.reshape(1).to(device=x.device, dtype=torch.float32) if isinstance(v, torch.Tensor) else _vdev(v, x.device)
+    if normal_op_supported(h, w) and not sens.requires_grad:
+        return NormalOpFn.apply(x, sens, _mask_u8(mask, b, t, h), vd)
+    k = sens_expand(x, sens, EXPAND_MASK, mask=mask)
+    return sens_reduce(k, sens) + vd * x

@@ -1,0 +1,153 @@
+/* b200sense — C ABI of the B200-native SENSE / data-consistency operators.
+ *
+ * Drop-in boundary for the hot path of f78bono/deep-cine-cardiac-mri.  The
+ * reference has no FFI layer: its boundary is the Python functional API
+ * (reconstruction/utils/__init__.py:1-25) plus the block methods listed below.
+ * Each entry point names the reference code it replaces (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - complex tensors are float32 with a trailing (re, im) pair, contiguous;
+ *   - k-space  (b,t,c,h,w,2) · image (b,t,h,w,2) · sens (b,c,h,w,2) ·
+ *     mask (b,t,h) uint8 (the reference's (b,t,1,h,1,1) flattened) ·
+ *     `v` = softplus(lambda) as ONE float in device memory (no host sync);
+ *   - the caller owns and pre-allocates all buffers, scratch included;
+ *   - `stream` is a cudaStream_t; calls only enqueue work (graph-capturable);
+ *   - `norm`: 0 "backward" (None), 1 "ortho", 2 "forward" (torch.fft meaning);
+ *   - return 0 on success, B2S_E* otherwise; b2s_last_error() gives the text.
+ *     No entry point ever falls back to a CPU or library path.
+ */
+#ifndef B200SENSE_H
+#define B200SENSE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_OK 0
+#define B2S_EINVAL 1       /* bad argument (null pointer, bad mode)            */
+#define B2S_EUNSUPPORTED 2 /* shape outside what the kernels implement         */
+#define B2S_ECUDA 3        /* CUDA runtime error (text in b2s_last_error)      */
+
+#define B2S_NORM_BACKWARD 0
+#define B2S_NORM_ORTHO 1
+#define B2S_NORM_FORWARD 2
+
+/* epilogue of b2s_sens_expand */
+#define B2S_EXPAND_PLAIN 0    /* k = F(S x)                      varnet.py:181-185          */
+#define B2S_EXPAND_MASK 1     /* k*m + 0.0                       cinenet.py:127-129, xpdnet.py:129-131 */
+#define B2S_EXPAND_DC 2       /* (1-m)k + m(k + v ref)/(1+v)     varnet.py:281-282, recurrent_varnet.py:86-89 */
+#define B2S_EXPAND_RESIDUAL 3 /* k*m - ref                       xpdnet.py:295-298 + 386-403 */
+
+/* input row weight of b2s_sens_reduce */
+#define B2S_REDUCE_PLAIN 0    /* A^H k                           varnet.py:187-194          */
+#define B2S_REDUCE_MASK 1     /* A^H (k*m)                       xpdnet.py:161-167          */
+#define B2S_REDUCE_DCGRAD 2   /* A^H (k*(1 - v/(1+v) m))         backward of B2S_EXPAND_DC  */
+
+int b2s_version(void);
+const char* b2s_last_error(void);
+/* 1 if (h,w) runs on the fused single-pass kernels, 0 if on the generic two-pass ones */
+int b2s_has_fused_plan(int h, int w);
+/* bytes of scratch b2s_sens_expand / b2s_sens_reduce need for this shape (0 for fused plans) */
+size_t b2s_scratch_bytes(int b, int t, int c, int h, int w);
+
+/* fft2c / ifft2c — utils/fftc.py:59-83, 86-110.  n_images centred 2-D transforms of h x w. */
+int b2s_fft2c(const float* in, float* out, int64_t n_images, int h, int w, int inverse, int norm,
+              void* stream);
+
+/* fft1c / ifft1c — utils/fftc.py:5-29, 32-56, and the XPDNet XF variant xpdnet.py:466,500.
+ * Layout (outer, n, inner, 2), transform over n (the callers' permuted views
+ * varnet.py:211-213,236-238 are this layout with inner = h*w).
+ * shift_in / shift_out: circular roll applied before / after the transform
+ * (fft1c: (n+1)/2, n/2 ; xpdnet.py:466: n/2, (n+1)/2). */
+int b2s_fft1c(const float* in, float* out, int64_t outer, int n, int64_t inner, int inverse, int norm,
+              int shift_in, int shift_out, void* stream);
+
+/* A — sens_expand fused with its consumer: varnet.py:181-185 (+281-282), cinenet.py:106-110 (+129),
+ * xpdnet.py:119-133, recurrent_varnet.py:65-69.  image (b,t,h,w,2), sens (b,c,h,w,2) ->
+ * kspace (b,t,c,h,w,2).  ref / mask / v may be NULL when the mode does not use them. */
+int b2s_sens_expand(const float* image, const float* sens, float* kspace, const float* ref,
+                    const uint8_t* mask, const float* v, int mode, int b, int t, int c, int h, int w,
+                    int norm, void* scratch, size_t scratch_bytes, void* stream);
+
+/* A^H — sens_reduce: varnet.py:187-194, cinenet.py:112-119, xpdnet.py:152-167, recurrent_*.py.
+ * over_frames == 0: out (b,t,h,w,2) = sum_c conj(mult[b,c]) * ifft2c(w(ky) k[b,t,c]),  mult = sens
+ * over_frames == 1: out (b,c,h,w,2) = sum_t conj(mult[b,t]) * ifft2c(w(ky) k[b,t,c]),  mult = image
+ *                   (gradient w.r.t. the sensitivity maps). */
+int b2s_sens_reduce(const float* kspace, const float* mult, float* out, const uint8_t* mask,
+                    const float* v, int weight_mode, int over_frames, int b, int t, int c, int h,
+                    int w, int norm, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Stand-alone soft data-consistency blend — varnet.py:281-282. n_bt = b*t. */
+int b2s_dc_blend(const float* kspace, const float* ref, const uint8_t* mask, const float* v,
+                 float* out, int64_t n_bt, int c, int h, int w, void* stream);
+/* Its backward: gk = g(1 - eta m), gref = g eta m (either may be NULL),
+ * gv[0] += sum g m (ref - out)/(1+v); gv must be zeroed by the caller. */
+int b2s_dc_blend_bwd(const float* g, const float* out, const float* ref, const uint8_t* mask,
+                     const float* v, float* gk, float* gref, float* gv, int64_t n_bt, int c, int h,
+                     int w, void* stream);
+
+/* utils/math.py:5-25 complex_mul with broadcasting: element strides (in complex
+ * elements, 0 = broadcast) over up to 6 leading dims; out is contiguous. conj_b: multiply by conj(b). */
+int b2s_complex_mul(const float* a, const float* b, float* out, int ndim, const int64_t* shape,
+                    const int64_t* stride_a, const int64_t* stride_b, int conj_b, void* stream);
+/* utils/math.py:28-45 / 48-62 / 65-79 on n contiguous complex elements */
+int b2s_complex_conj(const float* in, float* out, int64_t n, void* stream);
+int b2s_complex_abs(const float* in, float* out, int64_t n, int squared, void* stream);
+/* utils/coil_combine.py:5-18 / 21-34: sqrt(sum over r of x^2) on (outer, r, inner[,2]) */
+int b2s_rss(const float* in, float* out, int64_t outer, int64_t r, int64_t inner, int is_complex,
+            void* stream);
+
+/* SensitivityModel pre — varnet.py:64-71 / xpdnet.py:75-82: device-side ACS window from frame 0 of
+ * the mask, mean over t, rows outside the window zeroed (transforms.py:95-108).
+ * kspace (b,t,c,h,w,2) -> out (b,c,h,w,2).  window_out (optional, 2 ints per batch: pad, nlf). */
+int b2s_acs_mean(const float* kspace, const uint8_t* mask, float* out, int32_t* window_out, int b,
+                 int t, int c, int h, int w, void* stream);
+/* SensitivityModel post — varnet.py:58-59: x / rss_complex(x, coil dim) on (b,c,hw,2) */
+int b2s_rss_normalize(const float* in, float* out, int b, int c, int64_t hw, void* stream);
+/* backward of rss_normalize: gin = (g - x Re<g,x>_c / rss^2) / rss */
+int b2s_rss_normalize_bwd(const float* g, const float* in, float* gin, int b, int c, int64_t hw,
+                          void* stream);
+
+/* xfyf_transform head/tail — varnet.py:202-213, 232-241; cinenet.py:180-191, 210-219.
+ * pre:  image (b,t,hw,2) -> x = fft1c_t(image - mean_t) (xf != 0) or image - mean_t ; mean (b,hw,2)
+ * post: x (b,t,hw,2), mean -> ifft1c_t(x) + mean (xf != 0) or x + mean */
+int b2s_temporal_pre(const float* image, float* x, float* mean, int b, int t, int64_t hw, int xf,
+                     void* stream);
+int b2s_temporal_post(const float* x, const float* mean, float* out, int b, int t, int64_t hw, int xf,
+                      void* stream);
+
+/* CineNet normal operator and CG — cinenet.py:121-171, recurrent_cinenet.py:74-124.
+ * H x = A^H M A x + v x with the k-space kept on chip: because the mask only selects rows,
+ * F_w cancels and H x = sum_c conj(S_c) * (F_h^H M F_h)(S_c x) + v x.  x, out (b,t,h,w,2). */
+int b2s_normal_op(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out,
+                  int b, int t, int c, int h, int w, void* stream);
+/* CG scalar/vector kernels with alpha, beta kept in device memory (no .item() syncs):
+ * dot: out[0] = <a,b> over n floats (deterministic two-stage; scratch >= 1024 floats) */
+int b2s_dot(const float* a, const float* b, float* out, int64_t n, float* scratch, void* stream);
+/* y = y + (sign * num[0]/den[0]) * x */
+int b2s_axpy_ratio(float* y, const float* x, const float* num, const float* den, float sign,
+                   int64_t n, void* stream);
+/* p = r + (num[0]/den[0]) * p */
+int b2s_xpay_ratio(float* p, const float* r, const float* num, const float* den, int64_t n,
+                   void* stream);
+/* out = a + v[0]*b  (rhs and H x assembly) ; v may be NULL with scale used instead */
+int b2s_axpby(const float* a, const float* b, const float* v, float scale, float* out, int64_t n,
+              void* stream);
+
+/* End-to-end convenience with HOST buffers (pinned or pageable): one VarNet-style DC cascade
+ * k_next = DC(A(A^H k), ref) for a batch; copies in, runs, copies out on `stream`.
+ * Used for the e2e measurement; device workspace `ws` of b2s_dc_step_ws_bytes() bytes. */
+size_t b2s_dc_step_ws_bytes(int b, int t, int c, int h, int w);
+int b2s_dc_step_host(const float* kspace_host, const float* ref_host, const float* sens_host,
+                     const uint8_t* mask_host, float v_value, float* out_host, int b, int t, int c,
+                     int h, int w, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SENSE_H */

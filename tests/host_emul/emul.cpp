@@ -1,0 +1,82 @@
+// CPU emulation of the fused FFT kernels: compiles the very same host/device
+// phase functions with g++ and runs them sequentially.  Used by the not-gpu
+// tests to check the kernel index/twiddle math against the oracle without a GPU.
+#include <cstdint>
+#include "sense_functors.cuh"
+#include "fft2_kernel.cuh"
+
+using namespace b2s;
+typedef Plan<200, 200> P200;
+
+static float norm_scale(int h, int w, int inverse, int norm) {
+  // norm: 0 "backward", 1 "ortho", 2 "forward" (torch.fft semantics)
+  const double n = (double)h * w;
+  double s = 1.0;
+  if (norm == 1) s = 1.0 / sqrt(n);
+  else if ((norm == 0 && inverse) || (norm == 2 && !inverse)) s = 1.0 / n;
+  return (float)s;
+}
+
+extern "C" {
+
+int emu_fft2c(const float* in, float* out, long long n_images, int h, int w, int inverse, int norm) {
+  if (h != 200 || w != 200) return 2;
+  const float scale = norm_scale(h, w, inverse, norm) * centre_sign<P200>();
+  const long long hw = (long long)h * w;
+  if (inverse) {
+    ProPlain<200, true> pro{(const cfloat*)in, hw};
+    EpiPlain<200, true> epi{(cfloat*)out, hw};
+    fft2_half_emulate<P200>(pro, epi, scale, n_images);
+  } else {
+    ProPlain<200, false> pro{(const cfloat*)in, hw};
+    EpiPlain<200, false> epi{(cfloat*)out, hw};
+    fft2_half_emulate<P200>(pro, epi, scale, n_images);
+  }
+  return 0;
+}
+
+int emu_sens_expand(const float* img, const float* sens, float* kout, const float* ref, const uint8_t* mask,
+                    const float* v, int mode, int b, int t, int c, int h, int w, int norm) {
+  if (h != 200 || w != 200) return 2;
+  const float scale = norm_scale(h, w, 0, norm) * centre_sign<P200>();
+  const long long hw = (long long)h * w, n = (long long)b * t * c;
+  ProExpand<200> pro{(const cfloat*)img, (const cfloat*)sens, t, c, hw};
+#define RUN(M) { EpiKspace<200, M> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, h, hw}; \
+                 fft2_half_emulate<P200>(pro, epi, scale, n); }
+  if (mode == 0) RUN(0) else if (mode == 1) RUN(1) else if (mode == 2) RUN(2) else if (mode == 3) RUN(3) else return 1;
+#undef RUN
+  return 0;
+}
+
+int emu_sens_reduce(const float* k, const float* mult, float* out, const uint8_t* mask, const float* v, int wmode,
+                    int over_frames, int b, int t, int c, int h, int w, int norm) {
+  if (h != 200 || w != 200) return 2;
+  const float scale = norm_scale(h, w, 1, norm) * centre_sign<P200>();
+  const long long hw = (long long)h * w, n = (long long)b * t * c;
+  EpiReduce<200> epi;
+  epi.out = (cfloat*)out; epi.mult = (const cfloat*)mult; epi.T = t; epi.C = c;
+  if (!over_frames) {   // out (b,t,h,w) = sum_c conj(S[b,c]) y[b,t,c]
+    epi.os_b = t * hw; epi.os_t = hw; epi.os_c = 0; epi.ms_b = c * hw; epi.ms_t = 0; epi.ms_c = hw;
+    for (long long i = 0; i < (long long)b * t * hw * 2; ++i) out[i] = 0.f;
+  } else {              // out (b,c,h,w) = sum_t conj(X[b,t]) y[b,t,c]
+    epi.os_b = c * hw; epi.os_t = 0; epi.os_c = hw; epi.ms_b = t * hw; epi.ms_t = hw; epi.ms_c = 0;
+    for (long long i = 0; i < (long long)b * c * hw * 2; ++i) out[i] = 0.f;
+  }
+#define RUN(M) { ProKspace<200, M> pro{(const cfloat*)k, mask, v, c, h, hw}; fft2_half_emulate<P200>(pro, epi, scale, n); }
+  if (wmode == 0) RUN(0) else if (wmode == 1) RUN(1) else if (wmode == 2) RUN(2) else return 1;
+#undef RUN
+  return 0;
+}
+
+}  // extern "C"
+
+#include "normal_core.cuh"
+extern "C" int emu_normal_op(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out,
+                             int b, int t, int c, int h, int w) {
+  typedef NormalPlan<200, 20> P;
+  if (h != 200 || w % 20) return 2;
+  NormalArgs a; a.x = (const cfloat*)x; a.sens = (const cfloat*)sens; a.mask = mask; a.vptr = v; a.out = (cfloat*)out;
+  a.T = t; a.C = c; a.W = w;
+  normal_op_emulate<P>(a, (long long)b * t);
+  return 0;
+}

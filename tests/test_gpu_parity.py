@@ -1,0 +1,383 @@
+"""GPU parity: the CUDA path (through the C ABI via the ops layer) against the numpy oracle and
+the committed golden fixtures.  Tolerance: max|out - ref| / max|ref| <= 1e-5 (BASELINE.json
+north_star; fp64 oracle as arbiter).  Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+import torch
+
+import make_golden as G
+from oracle import sense_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from deep_cine_cardiac_mri_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def F():
+    from deep_cine_cardiac_mri_b200 import functional
+    return functional
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel(out, ref):
+    out = out.detach().cpu().numpy().astype(np.float64) if isinstance(out, torch.Tensor) else np.asarray(out, np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    return float(np.abs(out - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def f64(x):
+    return np.asarray(x, dtype=np.float64)
+
+
+# ------------------------------- functional tier ---------------------------- #
+@pytest.mark.parametrize("shape", [(3, 200, 200, 2), (1, 2, 3, 200, 200, 2), (2, 256, 256, 2), (2, 3, 12, 10, 2),
+                                   (3, 5, 7, 2), (1, 16, 16, 2), (2, 9, 8, 2), (4, 20, 30, 2), (1, 1, 1, 2),
+                                   (2, 17, 13, 2), (1, 320, 200, 2)])
+@pytest.mark.parametrize("norm", ["ortho", None, "forward"])
+def test_fft2c_ifft2c(F, shape, norm):
+    x = G.rng_normal(11, shape)
+    assert rel(F.fft2c(cu(x), norm=norm), O.fft2c(f64(x), norm=norm)) <= TOL
+    assert rel(F.ifft2c(cu(x), norm=norm), O.ifft2c(f64(x), norm=norm)) <= TOL
+
+
+@pytest.mark.parametrize("shape", [(3, 4, 15, 2), (2, 5, 16, 2), (2, 25, 2), (6, 17, 2), (2, 3, 30, 2), (5, 1, 2), (3, 29, 2)])
+def test_fft1c(F, shape):
+    x = G.rng_normal(12, shape)
+    assert rel(F.fft1c(cu(x)), O.fft1c(f64(x))) <= TOL
+    assert rel(F.ifft1c(cu(x)), O.ifft1c(f64(x))) <= TOL
+
+
+def test_fft1c_permuted_view_like_reference(F):
+    # varnet.py:211-213: (b,t,h,w,2).permute(0,2,3,1,4) -> fft1c -> permute back
+    x = G.rng_normal(13, (2, 15, 20, 24, 2))
+    xt = cu(x).permute(0, 2, 3, 1, 4)
+    assert not xt.is_contiguous()
+    out = F.fft1c(xt).permute(0, 3, 1, 2, 4)
+    ref = np.transpose(O.fft1c(np.transpose(f64(x), (0, 2, 3, 1, 4))), (0, 3, 1, 2, 4))
+    assert rel(out, ref) <= TOL
+    out = F.ifft1c(cu(x).unsqueeze(2).permute(0, 2, 3, 4, 1, 5)).permute(0, 4, 1, 2, 3, 5)
+    ref = np.transpose(O.ifft1c(np.transpose(f64(x)[:, :, None], (0, 2, 3, 4, 1, 5))), (0, 4, 1, 2, 3, 5))
+    assert rel(out, ref) <= TOL
+
+
+def test_noncontiguous_inputs(F):
+    x = G.rng_normal(14, (2, 200, 200, 4))
+    xs = cu(x)[..., 1:3]                                         # strided last dim
+    assert rel(F.fft2c(xs), O.fft2c(f64(x[..., 1:3]))) <= TOL
+    y = cu(G.rng_normal(15, (200, 3, 200, 2))).permute(1, 0, 2, 3)
+    assert rel(F.ifft2c(y), O.ifft2c(f64(y.cpu().numpy()))) <= TOL
+
+
+def test_pointwise_ops(F):
+    x = G.rng_normal(300, (2, 3, 5, 6, 2))
+    y = G.rng_normal(301, (2, 1, 5, 6, 2))
+    assert rel(F.complex_mul(cu(x), cu(y)), O.complex_mul(f64(x), f64(y))) <= 1e-6
+    assert rel(F.complex_mul(cu(y), cu(x)), O.complex_mul(f64(y), f64(x))) <= 1e-6
+    assert rel(F.complex_conj(cu(x)), O.complex_conj(f64(x))) == 0
+    assert rel(F.complex_abs(cu(x)), O.complex_abs(f64(x))) <= 1e-6
+    assert rel(F.complex_abs_sq(cu(x)), O.complex_abs_sq(f64(x))) <= 1e-6
+    for dim in (0, 1, 2, -3):
+        assert rel(F.rss(cu(x), dim=dim), O.rss(f64(x), dim=dim)) <= 1e-6
+    for dim in (0, 1, 2):
+        assert rel(F.rss_complex(cu(x), dim=dim), O.rss_complex(f64(x), dim=dim)) <= 1e-6
+    assert rel(F.fftshift(cu(x), dim=[-3, -2]), O.fftshift(x, dim=[-3, -2])) == 0
+    assert rel(F.ifftshift(cu(x)), O.ifftshift(x)) == 0
+    # SENSE broadcast pattern (b,t,1,h,w,2) x (b,1,c,h,w,2)
+    a, b = G.rng_normal(1, (2, 3, 1, 8, 6, 2)), G.rng_normal(2, (2, 1, 4, 8, 6, 2))
+    assert rel(F.complex_mul(cu(a), cu(b)), O.complex_mul(f64(a), f64(b))) <= 1e-6
+
+
+def test_empty_inputs(F):
+    assert F.fft2c(torch.zeros(0, 200, 200, 2, device="cuda")).shape == (0, 200, 200, 2)
+    assert F.fft2c(torch.zeros(0, 6, 4, 2, device="cuda")).shape == (0, 6, 4, 2)
+    assert F.complex_abs(torch.zeros(0, 2, device="cuda")).shape == (0,)
+
+
+def test_error_parity(F):
+    bad = torch.zeros(4, 4, 3, device="cuda")
+    for fn in (F.fft2c, F.ifft2c, F.fft1c, F.ifft1c, F.complex_conj, F.complex_abs, F.complex_abs_sq):
+        with pytest.raises(ValueError, match="Tensor does not have separate complex dim."):
+            fn(bad)
+    with pytest.raises(ValueError, match="Tensors do not have separate complex dim."):
+        F.complex_mul(bad, bad)
+    with pytest.raises(ValueError, match="len\\(shift\\) must match len\\(dim\\)"):
+        F.roll(bad, [1, 2], [0])
+    with pytest.raises(TypeError):
+        F.fft2c(torch.zeros(4, 4, 2, device="cuda", dtype=torch.float64))
+
+
+# --------------------------------- block tier ------------------------------- #
+CASES = {"a": (1, 3, 4, 200, 200), "rag": (2, 2, 3, 200, 200), "one": (1, 1, 1, 200, 200),
+         "g256": (1, 2, 3, 256, 256), "odd": (2, 3, 2, 18, 14)}
+
+
+def make_case(tag):
+    b, t, c, h, w = CASES[tag]
+    cs = G.sense_case(40 + h + c, b, t, c, h, w)
+    return cs, {k: (f64(v) if getattr(v, "dtype", None) == np.float32 and v.ndim else v) for k, v in cs.items()}
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_sens_expand_reduce_dc(ops, tag):
+    cs, d = make_case(tag)
+    img, k, ref, sens, mask = (cu(cs[n]) for n in ("img", "k", "ref", "sens", "mask"))
+    v = float(O.softplus(cs["lam"]))
+    kx = O.sens_expand(d["img"], d["sens"])
+    assert rel(ops.sens_expand(img, sens), kx) <= TOL
+    assert rel(ops.sens_expand(img, sens, ops.EXPAND_MASK, mask=mask), O.apply_mask(kx, d["mask"])) <= TOL
+    assert rel(ops.sens_expand(img, sens, ops.EXPAND_DC, ref=ref, mask=mask, v=v),
+               O.dc_blend(kx, d["ref"], d["mask"], v)) <= TOL
+    assert rel(ops.sens_expand(img, sens, ops.EXPAND_RESIDUAL, ref=ref, mask=mask),
+               O.apply_mask(kx, d["mask"]) - d["ref"]) <= TOL
+    assert rel(ops.sens_reduce(k, sens), O.sens_reduce(d["k"], d["sens"], keepdim=False)) <= TOL
+    assert rel(ops.sens_reduce(k, sens, mask=mask),
+               O.sens_reduce(O.apply_mask(d["k"], d["mask"]), d["sens"], keepdim=False)) <= TOL
+    assert rel(ops.dc_blend(k, ref, mask, v), O.dc_blend(d["k"], d["ref"], d["mask"], v)) <= 1e-6
+    # gradient-of-sens kernel: sum_t conj(x_t) ifft2c(k)
+    got = ops.raw_sens_reduce(k, img.squeeze(2).contiguous(), over_frames=True)
+    want = O.complex_mul(O.ifft2c(d["k"]), O.complex_conj(d["img"])).sum(axis=1)
+    assert rel(got, want) <= TOL
+
+
+@pytest.mark.parametrize("tag", ["a", "rag", "one"])
+def test_normal_op_and_cg(ops, tag):
+    from deep_cine_cardiac_mri_b200 import blocks
+    cs, d = make_case(tag)
+    img, ref, sens, mask = (cu(cs[n]) for n in ("img", "ref", "sens", "mask"))
+    v = float(O.softplus(cs["lam"]))
+    want = O.normal_op(d["img"], d["mask"], d["sens"], v)
+    assert rel(ops.normal_op(img.squeeze(2), sens, mask, v).unsqueeze(2), want) <= TOL
+    # composed path (used when sens needs grad / other sizes) agrees too
+    comp = ops.sens_reduce(ops.sens_expand(img, sens, ops.EXPAND_MASK, mask=mask), sens) + v * img.squeeze(2)
+    assert rel(comp.unsqueeze(2), want) <= TOL
+    import types
+    blk = types.SimpleNamespace(Softplus=torch.nn.Softplus(1.), lambda_reg=torch.tensor([float(cs["lam"])], device="cuda"))
+    rhs = O.sens_reduce(O.apply_mask(d["ref"], d["mask"]), d["sens"]) + v * d["img"]
+    got = blocks.conj_grad(blk, img, cu(rhs.astype(np.float32)), mask, sens, 4)
+    assert rel(got, O.conj_grad(d["img"], rhs, d["mask"], d["sens"], v, 4)) <= 5e-5
+
+
+def test_sens_model_and_temporal(ops):
+    from deep_cine_cardiac_mri_b200 import blocks
+    cs, d = make_case("a")
+    k, mask, img = cu(cs["k"]), cu(cs["mask"]), cu(cs["img"])
+    mk = O.apply_mask(d["k"], d["mask"])
+    pre = blocks._sens_pre(cu(mk.astype(np.float32)), mask)
+    want = O.sens_model_pre(mk, d["mask"])
+    assert rel(pre, want) <= TOL
+    assert rel(ops.RssNormalizeFn.apply(pre), O.divide_root_sum_of_squares(want)) <= 5e-5
+    for xf in (True, False):
+        x, mean = ops.TemporalPreFn.apply(img.squeeze(2), xf)
+        wx, wm = O.temporal_pre(d["img"][:, :, 0], xf)
+        assert rel(x, wx) <= TOL and rel(mean, wm) <= TOL
+        out = ops.TemporalPostFn.apply(img.squeeze(2), mean, xf)
+        assert rel(out.unsqueeze(2), O.temporal_post(d["img"], wm, xf)) <= TOL
+    ibuf = np.repeat(cs["img"], 5, axis=-1)
+    pk = np.concatenate([ibuf, ibuf[..., :1], ibuf[..., 5:6]], axis=-1)[:, :, 0]
+    assert rel(blocks.xpd_temporal_fft(cu(pk), 6), O.xpd_temporal_fft(f64(pk), 6)) <= TOL
+    assert rel(blocks.xpd_temporal_ifft(cu(ibuf[:, :, 0]), 5), O.xpd_temporal_ifft(f64(ibuf[:, :, 0]), 5)) <= TOL
+
+
+# ------------------------------- golden fixtures ---------------------------- #
+GOLD = np.load(G.HERE / "golden_v1.npz")
+
+
+def check_gold(name, tensor, tol=TOL):
+    flat = tensor.detach().cpu().numpy().astype(np.float64).ravel()
+    assert tuple(GOLD[f"{name}/shape"]) == tuple(tensor.shape), name
+    samp = GOLD[f"{name}/sample"].astype(np.float64)
+    got = flat[G.sample_index(flat.size)]
+    assert np.abs(got - samp).max() / max(np.abs(samp).max(), 1e-30) <= tol, name
+    assert abs((flat ** 2).sum() - GOLD[f"{name}/sumsq"]) <= 1e-4 * GOLD[f"{name}/sumsq"] + 1e-12, name
+
+
+@pytest.mark.parametrize("tag", list(G.BIG))
+def test_against_reference_golden(ops, F, tag):
+    from deep_cine_cardiac_mri_b200 import blocks
+    import types
+    b, t, c, h, w = G.BIG[tag]
+    cs = G.sense_case(1000 + len(tag) + h, b, t, c, h, w)
+    img, k, ref, sens, mask = (cu(cs[n]) for n in ("img", "k", "ref", "sens", "mask"))
+    lam = torch.tensor([float(cs["lam"])], device="cuda")
+    blk = types.SimpleNamespace(Softplus=torch.nn.Softplus(1.), lambda_reg=lam, dynamic_type="2D",
+                                model=torch.nn.Identity(), masked=True)
+    v = blk.Softplus(lam)
+    check_gold(f"{tag}/fft2c", F.fft2c(k))
+    check_gold(f"{tag}/ifft2c", F.ifft2c(k))
+    check_gold(f"{tag}/ifft2c_backward", F.ifft2c(k, norm=None))
+    check_gold(f"{tag}/sens_expand", blocks.sens_expand(blk, img, sens))
+    check_gold(f"{tag}/sens_reduce", blocks.sens_reduce(blk, k, sens))
+    check_gold(f"{tag}/dc_blend", ops.dc_blend(k, ref, mask, v))
+    check_gold(f"{tag}/normal_op", blocks.h_operator(blk, img, mask, sens))
+    rhs = blocks.sens_reduce(blk, ref * mask + 0.0, sens) + v * img
+    check_gold(f"{tag}/conj_grad", blocks.conj_grad(blk, img, rhs, mask, sens, 4), tol=5e-5)
+    ibuf = torch.repeat_interleave(img, 5, dim=-1)
+    check_gold(f"{tag}/xpd_forward", blocks.forward_operator_forward(blk, ibuf, mask, sens, 5))
+    check_gold(f"{tag}/xpd_backward", blocks.backward_operator_forward(blk, k, mask, sens, 1))
+    if b == 1:
+        check_gold(f"{tag}/varnet_block", blocks.varnet_block_forward(blk, k, ref, mask, sens))
+        mk = k * mask + 0.0
+        pre = blocks._sens_pre(mk, mask)
+        check_gold(f"{tag}/sens_model_pre", pre.unsqueeze(1))
+        check_gold(f"{tag}/sens_model", ops.RssNormalizeFn.apply(pre).unsqueeze(1), tol=5e-5)
+    x, mean = ops.TemporalPreFn.apply(img.squeeze(2), True)
+    check_gold(f"{tag}/temporal_pre", x)
+    check_gold(f"{tag}/temporal_post", ops.TemporalPostFn.apply(img.squeeze(2), mean, True).unsqueeze(2))
+    pk = torch.cat([ibuf, ibuf[..., :1], ibuf[..., 5:6]], dim=-1).squeeze(2)
+    check_gold(f"{tag}/xpd_tfft", blocks.xpd_temporal_fft(pk, 6))
+    check_gold(f"{tag}/xpd_tifft", blocks.xpd_temporal_ifft(ibuf.squeeze(2), 5))
+
+
+# ----------------------- size-independent properties at full size ----------- #
+@pytest.mark.parametrize("cfg", [(4, 15, 10, 200, 200), (1, 25, 20, 200, 200)])
+def test_properties_full_size(ops, F, cfg):
+    b, t, c, h, w = cfg
+    g = torch.Generator(device="cuda").manual_seed(0)
+    k = torch.randn(b, t, c, h, w, 2, device="cuda", generator=g)
+    x = torch.randn(b, t, h, w, 2, device="cuda", generator=g)
+    s = torch.randn(b, c, h, w, 2, device="cuda", generator=g)
+    s = s / s.pow(2).sum(dim=(1, 4), keepdim=True).sqrt()
+    # inverse / unitarity
+    rt = F.ifft2c(F.fft2c(k))
+    assert float((rt - k).abs().max() / k.abs().max()) <= TOL
+    assert abs(float(F.fft2c(k).pow(2).sum() / k.pow(2).sum()) - 1) <= 1e-5
+    # adjointness <A x, k> == <x, A^H k>
+    lhs = float((ops.sens_expand(x, s).double() * k.double()).sum())
+    rhs = float((x.double() * ops.sens_reduce(k, s).double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0) + 1e-2
+    # RSS == 1  =>  A^H A = I
+    back = ops.sens_reduce(ops.sens_expand(x, s), s)
+    assert float((back - x).abs().max() / x.abs().max()) <= TOL
+    # DC identity: blend == k - eta m (k - ref), and fused == unfused
+    m = torch.from_numpy(G.make_mask(3, b, t, h)).cuda()
+    v = 0.8
+    kx = ops.sens_expand(x, s)
+    fused = ops.sens_expand(x, s, ops.EXPAND_DC, ref=k, mask=m, v=v)
+    alt = kx - (v / (1 + v)) * m * (kx - k)
+    assert float((fused - alt).abs().max() / alt.abs().max()) <= TOL
+    assert float((fused - ops.dc_blend(kx, k, m, v)).abs().max()) <= 1e-6 * float(alt.abs().max())
+    # normal operator == A^H M A + v
+    hn = ops.normal_op(x, s, m, v)
+    comp = ops.sens_reduce(ops.sens_expand(x, s, ops.EXPAND_MASK, mask=m), s) + v * x
+    assert float((hn - comp).abs().max() / comp.abs().max()) <= TOL
+
+
+# ------------------------------------ autograd ------------------------------ #
+def _torch_ref_ops():
+    """plain torch (cuFFT) restatement used ONLY to check gradients"""
+    def fft2c(x):
+        z = torch.view_as_complex(x.contiguous())
+        z = torch.fft.fftshift(torch.fft.fftn(torch.fft.ifftshift(z, dim=(-2, -1)), dim=(-2, -1), norm="ortho"), dim=(-2, -1))
+        return torch.view_as_real(z)
+
+    def ifft2c(x):
+        z = torch.view_as_complex(x.contiguous())
+        z = torch.fft.fftshift(torch.fft.ifftn(torch.fft.ifftshift(z, dim=(-2, -1)), dim=(-2, -1), norm="ortho"), dim=(-2, -1))
+        return torch.view_as_real(z)
+
+    def cmul(x, y):
+        return torch.stack((x[..., 0] * y[..., 0] - x[..., 1] * y[..., 1], x[..., 0] * y[..., 1] + x[..., 1] * y[..., 0]), -1)
+
+    def conj(x):
+        return torch.stack((x[..., 0], -x[..., 1]), -1)
+    return fft2c, ifft2c, cmul, conj
+
+
+@pytest.mark.parametrize("hw", [(200, 200), (12, 10)])
+def test_autograd_matches_torch_reference(ops, hw):
+    h, w = hw
+    b, t, c = 1, 2, 3
+    fft2c, ifft2c, cmul, conj = _torch_ref_ops()
+    cs = G.sense_case(77, b, t, c, h, w)
+    mask = cu(cs["mask"])
+    mf = mask.float()
+
+    def leaves():
+        return [cu(cs[n]).requires_grad_(True) for n in ("img", "sens", "k", "ref")] + \
+               [torch.tensor([0.3], device="cuda", requires_grad=True)]
+
+    def run(ours):
+        img, sens, k, ref, lam = ls = leaves()
+        v = torch.nn.functional.softplus(lam)
+        if ours:
+            x1 = ops.sens_reduce(k, sens).unsqueeze(2)
+            out = ops.sens_expand(x1 + img, sens, ops.EXPAND_DC, ref=ref, mask=mask, v=v)
+            out2 = ops.sens_reduce(out, sens, mask=mask)
+        else:
+            x1 = cmul(ifft2c(k), conj(sens)).sum(2, keepdim=True)
+            kx = fft2c(cmul(x1 + img, sens))
+            out = (1 - mf) * kx + mf * (kx + v * ref) / (1 + v)
+            out2 = cmul(ifft2c(out * mf), conj(sens)).sum(2)
+        wgt = torch.linspace(0.5, 1.5, out2.numel(), device="cuda").view_as(out2)
+        loss = (out2 * wgt).sum() + (out * out).sum() * 0.1
+        loss.backward()
+        return [float(loss)] + [l.grad for l in ls]
+
+    a, r = run(True), run(False)
+    assert abs(a[0] - r[0]) <= 1e-4 * abs(r[0])
+    for ga, gr, name in zip(a[1:], r[1:], ("img", "sens", "k", "ref", "lam")):
+        assert ga is not None, name
+        err = float((ga - gr).abs().max() / gr.abs().max())
+        assert err <= 5e-5, (name, err)
+
+
+def test_autograd_fft_and_pointwise(ops, F):
+    fft2c, ifft2c, cmul, conj = _torch_ref_ops()
+    x = cu(G.rng_normal(5, (2, 200, 200, 2))).requires_grad_(True)
+    wgt = cu(G.rng_normal(6, (2, 200, 200, 2)))
+    for ours, ref in ((F.fft2c, fft2c), (F.ifft2c, ifft2c)):
+        g1, = torch.autograd.grad((ours(x) * wgt).sum(), x)
+        g2, = torch.autograd.grad((ref(x) * wgt).sum(), x)
+        assert float((g1 - g2).abs().max() / g2.abs().max()) <= TOL
+    a = cu(G.rng_normal(7, (2, 3, 1, 6, 5, 2))).requires_grad_(True)
+    bb = cu(G.rng_normal(8, (2, 1, 4, 6, 5, 2))).requires_grad_(True)
+    l1 = (F.complex_abs(F.complex_mul(a, F.complex_conj(bb))) ** 2).sum() + F.rss_complex(F.complex_mul(a, bb), dim=2).sum()
+    ga, gb = torch.autograd.grad(l1, (a, bb))
+    prod = cmul(a, conj(bb))
+    l2 = ((prod ** 2).sum(-1).sqrt() ** 2).sum() + (cmul(a, bb) ** 2).sum(-1).sum(2).sqrt().sum()
+    ra, rb = torch.autograd.grad(l2, (a, bb))
+    assert float((ga - ra).abs().max() / ra.abs().max()) <= 1e-5
+    assert float((gb - rb).abs().max() / rb.abs().max()) <= 1e-5
+    # temporal transforms
+    z = cu(G.rng_normal(9, (1, 15, 8, 6, 2))).requires_grad_(True)
+    w2 = cu(G.rng_normal(10, (1, 15, 8, 6, 2)))
+    xx, mean = ops.TemporalPreFn.apply(z, True)
+    out = ops.TemporalPostFn.apply(xx * 2.0, mean, True)
+    g1, = torch.autograd.grad((out * w2).sum(), z)
+    zc = torch.view_as_complex(z)
+    mu = zc.mean(1, keepdim=True)
+    tt = torch.fft.fftshift(torch.fft.fft(torch.fft.ifftshift(zc - mu, dim=1), dim=1, norm="ortho"), dim=1) * 2.0
+    oo = torch.fft.fftshift(torch.fft.ifft(torch.fft.ifftshift(tt, dim=1), dim=1, norm="ortho"), dim=1) + mu
+    g2, = torch.autograd.grad((torch.view_as_real(oo) * w2).sum(), z)
+    assert float((g1 - g2).abs().max() / g2.abs().max()) <= 1e-5
+
+
+def test_dc_step_host_entry():
+    """the e2e C-ABI entry point with HOST buffers (b2s_dc_step_host)"""
+    import ctypes as C
+    from deep_cine_cardiac_mri_b200 import _lib
+    lib = _lib.lib()
+    b, t, c, h, w = 1, 2, 3, 200, 200
+    cs = G.sense_case(123, b, t, c, h, w)
+    v = 0.9
+    ws_bytes = lib.b2s_dc_step_ws_bytes(b, t, c, h, w)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    out = np.empty_like(cs["k"])
+    P = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    mask = np.ascontiguousarray(cs["mask"].reshape(b, t, h))
+    rc = lib.b2s_dc_step_host(P(cs["k"]), P(cs["ref"]), P(np.ascontiguousarray(cs["sens"])), P(mask), v, P(out),
+                              b, t, c, h, w, C.c_void_p(ws.data_ptr()), ws_bytes, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.b2s_last_error()
+    torch.cuda.synchronize()
+    want = O.varnet_block(f64(cs["k"]), f64(cs["ref"]), cs["mask"], f64(cs["sens"]), v)
+    assert rel(out, want) <= TOL
