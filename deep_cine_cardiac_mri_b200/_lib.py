@@ -12,7 +12,7 @@ import subprocess
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libb2sense.so"
+LIB_PATH = Path(os.environ["B2S_LIB"]) if os.environ.get("B2S_LIB") else PKG / "lib" / "libb2sense.so"
 _lib = None
 
 _p, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t

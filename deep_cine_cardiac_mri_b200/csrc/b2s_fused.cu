@@ -1,5 +1,6 @@
 // Fused single-pass SENSE operators on the plan sizes (200 x 200) and their
 // composition from the generic kernels for every other size.
+#include <stdlib.h>
 #include "b2s_common.cuh"
 #include "sense_functors.cuh"
 #include "fft2_kernel.cuh"
@@ -8,19 +9,36 @@ using namespace b2s;
 
 namespace {
 
-typedef Plan<200, 200> P200;
+typedef Plan<200, 200, 256, 1> P200;    // 8 warps x 255 registers, 64-bit global accesses
+typedef Plan<200, 200, 512, 1> P200N;   // experimental: 16 warps x 128 registers, 64-bit accesses
+
+int plan_threads() {
+  static int nt = 0;
+  if (!nt) { const char* e = getenv("B2S_NT"); nt = (e && atoi(e) == 512) ? 512 : 256; }
+  return nt;
+}
 
 template <class P, class Pro, class Epi>
 int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st) {
   if (n_images <= 0) return B2S_OK;
   if (2 * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
   auto kern = fft2_half_kernel<P, Pro, Epi>;
-  static bool configured = false;            // per instantiation; idempotent attribute
-  if (!configured) {
+  int dev = 0, sms = 0;
+  B2S_CUDA(cudaGetDevice(&dev));
+  static int sm_count[64] = {0};             // immutable per-device facts
+  static bool configured[64] = {false};      // per instantiation and device
+  if (dev < 0 || dev >= 64) return fail(B2S_EUNSUPPORTED, "device index >= 64");
+  if (!sm_count[dev]) B2S_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+  sms = sm_count[dev];
+  if (!configured[dev]) {
     B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<P>::SMEM_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
-  kern<<<(unsigned)(2 * n_images), P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale);
+  const int n_items = (int)(2 * n_images);
+  const unsigned grid = (unsigned)(n_items < sms ? n_items : sms);   // persistent: one CTA per SM
+  static int stagger = -1;
+  if (stagger < 0) { const char* e = getenv("B2S_STAGGER_NS"); stagger = e ? atoi(e) : 0; }
+  kern<<<grid, P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale, n_items, (unsigned)stagger);
   return check_launch("fft2_half_kernel");
 }
 
@@ -35,20 +53,22 @@ extern "C" size_t b2s_scratch_bytes(int b, int t, int c, int h, int w) {
 
 extern "C" int b2s_fft2c(const float* in, float* out, int64_t n_images, int h, int w, int inverse,
                          int norm, void* stream) {
-  if (!in || !out || h <= 0 || w <= 0 || n_images < 0 || bad_norm(norm)) return fail(B2S_EINVAL, "b2s_fft2c: bad argument");
+  if (h <= 0 || w <= 0 || n_images < 0 || bad_norm(norm)) return fail(B2S_EINVAL, "b2s_fft2c: bad argument");
+  if (n_images == 0) return B2S_OK;
+  if (!in || !out) return fail(B2S_EINVAL, "b2s_fft2c: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = norm_scale(h, w, inverse, norm);
   if (h == 200 && w == 200) {
     const long long hw = 40000;
     const float s = scale * centre_sign<P200>();
     if (inverse) {
-      ProPlain<200, true> pro{(const cfloat*)in, hw};
-      EpiPlain<200, true> epi{(cfloat*)out, hw};
-      return launch_fused<P200>(pro, epi, s, n_images, st);
+      ProPlain<200, 200, true> pro{(const cfloat*)in, hw};
+      EpiPlain<200, 200, true> epi{(cfloat*)out, hw};
+      return (plan_threads() == 512) ? launch_fused<P200N>(pro, epi, s, n_images, st) : launch_fused<P200>(pro, epi, s, n_images, st);
     }
-    ProPlain<200, false> pro{(const cfloat*)in, hw};
-    EpiPlain<200, false> epi{(cfloat*)out, hw};
-    return launch_fused<P200>(pro, epi, s, n_images, st);
+    ProPlain<200, 200, false> pro{(const cfloat*)in, hw};
+    EpiPlain<200, 200, false> epi{(cfloat*)out, hw};
+    return (plan_threads() == 512) ? launch_fused<P200N>(pro, epi, s, n_images, st) : launch_fused<P200>(pro, epi, s, n_images, st);
   }
   return generic_fft2(in, out, n_images, h, w, inverse, scale, st);
 }
@@ -57,8 +77,10 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
                                const uint8_t* mask, const float* v, int mode, int b, int t, int c,
                                int h, int w, int norm, void* scratch, size_t scratch_bytes, void* stream) {
   (void)scratch; (void)scratch_bytes;
-  if (!image || !sens || !kspace || b < 0 || t < 0 || c < 0 || bad_norm(norm) || mode < 0 || mode > 3)
+  if (b < 0 || t < 0 || c < 0 || bad_norm(norm) || mode < 0 || mode > 3)
     return fail(B2S_EINVAL, "b2s_sens_expand: bad argument");
+  if ((int64_t)b * t * c == 0) return B2S_OK;
+  if (!image || !sens || !kspace) return fail(B2S_EINVAL, "b2s_sens_expand: null pointer");
   if ((mode >= 1 && !mask) || (mode >= 2 && !ref) || (mode == 2 && !v))
     return fail(B2S_EINVAL, "b2s_sens_expand: mode needs mask/ref/v");
   cudaStream_t st = (cudaStream_t)stream;
@@ -67,11 +89,11 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
   if (h == 200 && w == 200) {
     const long long hw = 40000;
     const float s = scale * centre_sign<P200>();
-    ProExpand<200> pro{(const cfloat*)image, (const cfloat*)sens, t, c, hw};
+    ProExpand<200, 200> pro{(const cfloat*)image, (const cfloat*)sens, t, c, hw};
 #define B2S_RUN(M)                                                                            \
   {                                                                                           \
-    EpiKspace<200, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, h, hw};            \
-    return launch_fused<P200>(pro, epi, s, n, st);                                            \
+    EpiKspace<200, 200, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};            \
+    return (plan_threads() == 512) ? launch_fused<P200N>(pro, epi, s, n, st) : launch_fused<P200>(pro, epi, s, n, st);                                          \
   }
     switch (mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) case 2: B2S_RUN(2) default: B2S_RUN(3) }
 #undef B2S_RUN
@@ -88,8 +110,10 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
 extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* out, const uint8_t* mask,
                                const float* v, int weight_mode, int over_frames, int b, int t, int c,
                                int h, int w, int norm, void* scratch, size_t scratch_bytes, void* stream) {
-  if (!kspace || !mult || !out || b < 0 || t < 0 || c < 0 || bad_norm(norm) || weight_mode < 0 || weight_mode > 2)
+  if (b < 0 || t < 0 || c < 0 || bad_norm(norm) || weight_mode < 0 || weight_mode > 2)
     return fail(B2S_EINVAL, "b2s_sens_reduce: bad argument");
+  if ((over_frames ? (int64_t)b * c : (int64_t)b * t) == 0) return B2S_OK;
+  if (!out || ((int64_t)b * t * c > 0 && (!kspace || !mult))) return fail(B2S_EINVAL, "b2s_sens_reduce: null pointer");
   if ((weight_mode >= 1 && !mask) || (weight_mode == 2 && !v))
     return fail(B2S_EINVAL, "b2s_sens_reduce: weight mode needs mask/v");
   cudaStream_t st = (cudaStream_t)stream;
@@ -102,14 +126,14 @@ extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* ou
     B2S_CUDA(cudaMemsetAsync(out, 0, (size_t)out_images * hw * 2 * sizeof(float), st));
     if (n == 0) return B2S_OK;
     const float s = scale * centre_sign<P200>();
-    EpiReduce<200> epi;
+    EpiReduce<200, 200> epi;
     epi.out = (cfloat*)out; epi.mult = (const cfloat*)mult; epi.T = t; epi.C = c;
     if (!over_frames) { epi.os_b = t * hw; epi.os_t = hw; epi.os_c = 0; epi.ms_b = c * hw; epi.ms_t = 0; epi.ms_c = hw; }
     else              { epi.os_b = c * hw; epi.os_t = 0; epi.os_c = hw; epi.ms_b = t * hw; epi.ms_t = hw; epi.ms_c = 0; }
 #define B2S_RUN(M)                                                            \
   {                                                                           \
-    ProKspace<200, M> pro{(const cfloat*)kspace, mask, v, c, h, hw};          \
-    return launch_fused<P200>(pro, epi, s, n, st);                            \
+    ProKspace<200, 200, M> pro{(const cfloat*)kspace, mask, v, c, hw};          \
+    return (plan_threads() == 512) ? launch_fused<P200N>(pro, epi, s, n, st) : launch_fused<P200>(pro, epi, s, n, st);                          \
   }
     switch (weight_mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) default: B2S_RUN(2) }
 #undef B2S_RUN
@@ -169,3 +193,12 @@ extern "C" int b2s_dc_step_host(const float* kspace_host, const float* ref_host,
   B2S_CUDA(cudaMemcpyAsync(out_host, dout, K, cudaMemcpyDeviceToHost, st));
   return B2S_OK;
 }
+
+#ifdef B2S_PHASE_TIMING
+extern "C" int b2s_debug_phase_cycles(unsigned long long* out_host, int reset) {
+  B2S_CUDA(cudaDeviceSynchronize());
+  B2S_CUDA(cudaMemcpyFromSymbol(out_host, b2s::g_phase_cycles, 8 * sizeof(unsigned long long)));
+  if (reset) { unsigned long long z[8] = {0}; B2S_CUDA(cudaMemcpyToSymbol(b2s::g_phase_cycles, z, sizeof(z))); }
+  return B2S_OK;
+}
+#endif

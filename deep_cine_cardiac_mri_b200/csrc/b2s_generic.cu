@@ -166,7 +166,9 @@ int generic_fft2(const float* in, float* out, int64_t n_images, int h, int w, in
 
 extern "C" int b2s_fft1c(const float* in, float* out, int64_t outer, int n, int64_t inner, int inverse,
                          int norm, int shift_in, int shift_out, void* stream) {
-  if (!in || !out || outer < 0 || inner < 0 || n < 1 || bad_norm(norm)) return fail(B2S_EINVAL, "b2s_fft1c: bad argument");
+  if (outer < 0 || inner < 0 || n < 1 || bad_norm(norm)) return fail(B2S_EINVAL, "b2s_fft1c: bad argument");
+  if (outer * inner == 0) return B2S_OK;
+  if (!in || !out) return fail(B2S_EINVAL, "b2s_fft1c: null pointer");
   float scale = 1.f;
   if (norm == B2S_NORM_ORTHO) scale = (float)(1.0 / sqrt((double)n));
   else if ((norm == B2S_NORM_BACKWARD && inverse) || (norm == B2S_NORM_FORWARD && !inverse)) scale = 1.f / (float)n;

@@ -89,36 +89,62 @@ __global__ void coil_reduce_kernel(const cfloat* y, const cfloat* mult, cfloat* 
 }
 
 // ------------------------------- DC blend ---------------------------------- //
-__global__ void dc_blend_kernel(const float4* k, const float4* ref, const uint8_t* mask, const float* vptr,
-                                float4* out, int C, int H, int W2, long long n4) {
+// V = float4 (two complex per thread, even w) or cfloat (odd w)
+template <class V> struct VecOps;
+template <> struct VecOps<float4> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void get(const float4& v, float* f) { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+  static __device__ __forceinline__ float4 put(const float* f) { return make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct VecOps<cfloat> {
+  static constexpr int N = 2;
+  static __device__ __forceinline__ void get(const cfloat& v, float* f) { f[0] = v.x; f[1] = v.y; }
+  static __device__ __forceinline__ cfloat put(const float* f) { return make_c(f[0], f[1]); }
+};
+
+template <class V>
+__global__ void dc_blend_kernel(const V* k, const V* ref, const uint8_t* mask, const float* vptr, V* out, int C, int H,
+                                int WV, long long nv) {
   const float v = *vptr;
-  GRID_STRIDE(i, n4) {                                 // one float4 = 2 complex
-    const long long row = i / W2, y = row % H, bt = row / H / C;
-    float4 z = k[i];
+  GRID_STRIDE(i, nv) {
+    const long long row = i / WV, y = row % H, bt = row / H / C;
+    float z[VecOps<V>::N], r[VecOps<V>::N];
+    VecOps<V>::get(k[i], z);
     if (mask[bt * H + y]) {
-      const float4 r = ref[i];
-      z.x = (z.x + v * r.x) / (1.f + v); z.y = (z.y + v * r.y) / (1.f + v);
-      z.z = (z.z + v * r.z) / (1.f + v); z.w = (z.w + v * r.w) / (1.f + v);
+      VecOps<V>::get(ref[i], r);
+#pragma unroll
+      for (int e = 0; e < VecOps<V>::N; ++e) z[e] = (z[e] + v * r[e]) / (1.f + v);
     }
-    out[i] = z;
+    out[i] = VecOps<V>::put(z);
   }
 }
 
-__global__ void dc_blend_bwd_kernel(const float4* g, const float4* outv, const float4* ref, const uint8_t* mask,
-                                    const float* vptr, float4* gk, float4* gref, float* gv, int C, int H, int W2,
-                                    long long n4) {
+template <class V>
+__global__ void dc_blend_bwd_kernel(const V* g, const V* outv, const V* ref, const uint8_t* mask, const float* vptr,
+                                    V* gk, V* gref, float* gv, int C, int H, int WV, long long nv) {
   const float v = *vptr, eta = v / (1.f + v), inv1 = 1.f / (1.f + v);
   float acc = 0.f;
-  GRID_STRIDE(i, n4) {
-    const long long row = i / W2, y = row % H, bt = row / H / C;
-    const float4 gg = g[i];
+  GRID_STRIDE(i, nv) {
+    const long long row = i / WV, y = row % H, bt = row / H / C;
+    float gg[VecOps<V>::N], t[VecOps<V>::N];
+    VecOps<V>::get(g[i], gg);
     const bool m = mask[bt * H + y] != 0;
     const float a = m ? (1.f - eta) : 1.f, bb = m ? eta : 0.f;
-    if (gk) gk[i] = make_float4(gg.x * a, gg.y * a, gg.z * a, gg.w * a);
-    if (gref) gref[i] = make_float4(gg.x * bb, gg.y * bb, gg.z * bb, gg.w * bb);
+    if (gk) {
+#pragma unroll
+      for (int e = 0; e < VecOps<V>::N; ++e) t[e] = gg[e] * a;
+      gk[i] = VecOps<V>::put(t);
+    }
+    if (gref) {
+#pragma unroll
+      for (int e = 0; e < VecOps<V>::N; ++e) t[e] = gg[e] * bb;
+      gref[i] = VecOps<V>::put(t);
+    }
     if (gv && m) {
-      const float4 r = ref[i], o = outv[i];
-      acc += (gg.x * (r.x - o.x) + gg.y * (r.y - o.y) + gg.z * (r.z - o.z) + gg.w * (r.w - o.w)) * inv1;
+      float r[VecOps<V>::N], o[VecOps<V>::N];
+      VecOps<V>::get(ref[i], r); VecOps<V>::get(outv[i], o);
+#pragma unroll
+      for (int e = 0; e < VecOps<V>::N; ++e) acc += gg[e] * (r[e] - o[e]) * inv1;
     }
   }
   if (gv) {
@@ -336,51 +362,61 @@ int launch_coil_reduce(const float* y, const float* mult, float* out, int over_f
 
 extern "C" int b2s_dc_blend(const float* kspace, const float* ref, const uint8_t* mask, const float* v, float* out,
                             int64_t n_bt, int c, int h, int w, void* stream) {
-  if (!kspace || !ref || !mask || !v || !out || (w & 1)) return fail(w & 1 ? B2S_EUNSUPPORTED : B2S_EINVAL, "b2s_dc_blend: bad argument (w must be even)");
-  const long long n4 = n_bt * c * h * (w / 2);
-  if (n4 == 0) return B2S_OK;
-  dc_blend_kernel<<<grid_for(n4), NT, 0, (cudaStream_t)stream>>>((const float4*)kspace, (const float4*)ref, mask, v, (float4*)out, c, h, w / 2, n4);
+  const long long n = n_bt * c * h * (long long)w;
+  if (n == 0) return B2S_OK;
+  if (!kspace || !ref || !mask || !v || !out) return fail(B2S_EINVAL, "b2s_dc_blend: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w % 2 == 0)
+    dc_blend_kernel<float4><<<grid_for(n / 2), NT, 0, st>>>((const float4*)kspace, (const float4*)ref, mask, v, (float4*)out, c, h, w / 2, n / 2);
+  else
+    dc_blend_kernel<cfloat><<<grid_for(n), NT, 0, st>>>((const cfloat*)kspace, (const cfloat*)ref, mask, v, (cfloat*)out, c, h, w, n);
   return check_launch("dc_blend_kernel");
 }
 
 extern "C" int b2s_dc_blend_bwd(const float* g, const float* out, const float* ref, const uint8_t* mask, const float* v,
                                 float* gk, float* gref, float* gv, int64_t n_bt, int c, int h, int w, void* stream) {
-  if (!g || !mask || !v || (gv && (!out || !ref)) || (w & 1)) return fail(B2S_EINVAL, "b2s_dc_blend_bwd: bad argument");
-  const long long n4 = n_bt * c * h * (w / 2);
-  if (n4 == 0) return B2S_OK;
-  dc_blend_bwd_kernel<<<grid_for(n4), NT, 0, (cudaStream_t)stream>>>((const float4*)g, (const float4*)out, (const float4*)ref, mask, v,
-                                                                     (float4*)gk, (float4*)gref, gv, c, h, w / 2, n4);
+  const long long n = n_bt * c * h * (long long)w;
+  if (n == 0) return B2S_OK;
+  if (!g || !mask || !v || (gv && (!out || !ref))) return fail(B2S_EINVAL, "b2s_dc_blend_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w % 2 == 0)
+    dc_blend_bwd_kernel<float4><<<grid_for(n / 2), NT, 0, st>>>((const float4*)g, (const float4*)out, (const float4*)ref, mask, v,
+                                                                (float4*)gk, (float4*)gref, gv, c, h, w / 2, n / 2);
+  else
+    dc_blend_bwd_kernel<cfloat><<<grid_for(n), NT, 0, st>>>((const cfloat*)g, (const cfloat*)out, (const cfloat*)ref, mask, v,
+                                                            (cfloat*)gk, (cfloat*)gref, gv, c, h, w, n);
   return check_launch("dc_blend_bwd_kernel");
 }
 
 extern "C" int b2s_complex_mul(const float* a, const float* b, float* out, int ndim, const int64_t* shape,
                                const int64_t* stride_a, const int64_t* stride_b, int conj_b, void* stream) {
-  if (!a || !b || !out || ndim < 0 || ndim > 6 || (ndim && (!shape || !stride_a || !stride_b))) return fail(B2S_EINVAL, "b2s_complex_mul: bad argument");
+  if (ndim < 0 || ndim > 6 || (ndim && (!shape || !stride_a || !stride_b))) return fail(B2S_EINVAL, "b2s_complex_mul: bad argument");
   MulDims d; d.nd = ndim; long long n = 1;
   for (int k = 0; k < 6; ++k) { d.shape[k] = 1; d.sa[k] = 0; d.sb[k] = 0; }
   for (int k = 0; k < ndim; ++k) { d.shape[k] = shape[k]; d.sa[k] = stride_a[k]; d.sb[k] = stride_b[k]; n *= shape[k]; }
   if (n == 0) return B2S_OK;
+  if (!a || !b || !out) return fail(B2S_EINVAL, "b2s_complex_mul: null pointer");
   complex_mul_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>((const cfloat*)a, (const cfloat*)b, (cfloat*)out, d, conj_b, n);
   return check_launch("complex_mul_kernel");
 }
 
 extern "C" int b2s_complex_conj(const float* in, float* out, int64_t n, void* stream) {
-  if (!in || !out) return fail(B2S_EINVAL, "b2s_complex_conj: null pointer");
   if (n == 0) return B2S_OK;
+  if (!in || !out) return fail(B2S_EINVAL, "b2s_complex_conj: null pointer");
   complex_conj_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>((const cfloat*)in, (cfloat*)out, n);
   return check_launch("complex_conj_kernel");
 }
 
 extern "C" int b2s_complex_abs(const float* in, float* out, int64_t n, int squared, void* stream) {
-  if (!in || !out) return fail(B2S_EINVAL, "b2s_complex_abs: null pointer");
   if (n == 0) return B2S_OK;
+  if (!in || !out) return fail(B2S_EINVAL, "b2s_complex_abs: null pointer");
   complex_abs_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>((const cfloat*)in, out, n, squared);
   return check_launch("complex_abs_kernel");
 }
 
 extern "C" int b2s_rss(const float* in, float* out, int64_t outer, int64_t r, int64_t inner, int is_complex, void* stream) {
-  if (!in || !out) return fail(B2S_EINVAL, "b2s_rss: null pointer");
   if (outer * inner == 0) return B2S_OK;
+  if (!in || !out) return fail(B2S_EINVAL, "b2s_rss: null pointer");
   rss_kernel<<<grid_for(outer * inner), NT, 0, (cudaStream_t)stream>>>(in, out, outer, r, inner, is_complex);
   return check_launch("rss_kernel");
 }

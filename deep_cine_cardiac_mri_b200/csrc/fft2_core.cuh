@@ -1,18 +1,19 @@
 // Fused centred 2-D FFT core ("half-split" design) — host/device phase functions.
 //
-// One CTA produces HALF of the output rows of one H x W coil image (output rows
-// ky == q mod 2) from ALL of its input rows, entirely on chip:
+// One work item produces HALF of the output rows of one H x W coil image (output
+// rows ky == q mod 2) from ALL of its input rows, entirely on chip:
 //
-//   Phase A  load 8 rows {g + G*j} x R columns {x0 + X0*i} per task straight from
-//            global memory into registers (prologue functor = identity | S*x |
-//            k-space row weight), radix-8 DIF butterfly over the 8 rows pruned to
-//            the 4 outputs of parity q, row twiddle, radix-R butterfly over the
-//            R columns, column twiddle, store to the shared buffer B.
+//   Phase A  load 8 rows {g + G*j} x R column groups {x0 + X0*i} per task straight
+//            from global memory into registers with 128-bit accesses (NC = 2 adjacent
+//            columns per thread; prologue functor = identity | S*x | k-space row
+//            weight), radix-8 DIF butterfly over the 8 rows pruned to the 4 outputs
+//            of parity q, row twiddle, radix-R butterfly over the R columns, column
+//            twiddle, store to the shared buffer B.
 //   Phase B  X0-point register codelet along w per (row, k1); rewrites the row in
 //            natural kx order.
-//   Phase C  G-point register codelet along h per (m-block, kx); results leave
-//            through the epilogue functor (plain store | mask / soft-DC blend with
-//            the reference k-space | conj(S)-multiply + coil reduction).
+//   Phase C  G-point register codelet along h per (m-block, kx pair); results leave
+//            through the epilogue functor with 128-bit accesses (plain store | mask /
+//            soft-DC blend with the reference k-space | conj(S)-multiply + coil sum).
 //
 // The centring (fftshift/ifftshift of utils/fftc.py:59-110) is folded in: for
 // even sizes fft2c(x) = chk * FFT2(chk * x) with chk = (-1)^(y+x); the input
@@ -29,6 +30,8 @@
 namespace b2s {
 
 struct alignas(8) cfloat { float x, y; };
+// NC adjacent complex values moved with one (64- or 128-bit) access
+template <int NC> struct alignas(8 * NC) cvec { cfloat v[NC]; };
 
 B2S_HD cfloat make_c(float a, float b) { cfloat r; r.x = a; r.y = b; return r; }
 
@@ -49,35 +52,37 @@ B2S_HD cfloat twiddle(int n, int N) {
 // --------------------------------------------------------------------------- //
 // plans
 // --------------------------------------------------------------------------- //
-template <int H_, int W_> struct Plan;
+template <int H_, int W_, int NT_ = 256, int NC_ = 2> struct Plan;
 
 // 200 x 200 (dataset crop, data/mri_data.py:273-277): h = 8*25, w = 5*40
-template <> struct Plan<200, 200> {
+template <int NT_, int NC_> struct Plan<200, 200, NT_, NC_> {
   static constexpr int H = 200, W = 200;
   static constexpr int G = 25;        // Phase C codelet size, H = 8*G
   static constexpr int R = 5;         // Phase A column radix, W = R*X0
   static constexpr int X0 = 40;       // Phase B codelet size
   static constexpr int SEG = 41;      // padded k1-segment pitch (complex) written by Phase A
   static constexpr int PITCH = 213;   // row pitch of B (complex); 213 = 5 mod 16 keeps Phase B conflict-free
-  static constexpr int NT = 512;
+  static constexpr int NT = NT_;      // threads per CTA
+  static constexpr int NC = NC_;      // adjacent columns per thread in Phases A and C (global access = 8*NC bytes)
 };
-
-// 160 x 160 and 200 x 160 style plans can be added here when needed.
 
 template <class P> struct Derived {
   static constexpr int ROWS = 4 * P::G;                         // rows of B (half image)
   static constexpr int SG = P::G & 1;                           // (-1)^(G j) relabel
   static constexpr int B_ELEMS = ROWS * P::PITCH;               // complex elements
   static constexpr int TW_OFF = B_ELEMS;                        // TW[W]
-  static constexpr int TH_OFF = TW_OFF + P::W;                  // TH[G][4]
-  static constexpr int SMEM_ELEMS = TH_OFF + P::G * 4;
+  static constexpr int TH_OFF = TW_OFF + P::W;                  // TH[2][G][4] (both halves q)
+  static constexpr int SMEM_ELEMS = TH_OFF + 2 * P::G * 4;
   static constexpr int SMEM_BYTES = SMEM_ELEMS * 8;
-  static constexpr int TASKS_A = P::G * P::X0;
-  static constexpr int TASKS_C = 4 * P::W;
+  static constexpr int XP = P::X0 / P::NC;                      // column groups per row group
+  static constexpr int TASKS_A = P::G * XP;
+  static constexpr int KXP = P::W / P::NC;
+  static constexpr int TASKS_C = 4 * KXP;
   static constexpr int RPR = (P::NT / P::R) < ROWS ? (P::NT / P::R) : ROWS;   // rows per Phase-B round
   static constexpr int ROUNDS_B = (ROWS + RPR - 1) / RPR;
   static_assert(P::H == 8 * P::G && P::W == P::R * P::X0, "bad plan");
   static_assert((P::X0 & 1) == 0, "X0 must be even (sign folding)");
+  static_assert(P::X0 % P::NC == 0 && P::W % P::NC == 0, "NC must divide X0 and W");
   static_assert(P::R * P::SEG <= P::PITCH && P::W <= P::PITCH, "pitch too small");
 };
 
@@ -87,11 +92,11 @@ template <class P> B2S_HD int m_of(int r, int q) { return (2 * r + q + 4 * Deriv
 // --------------------------------------------------------------------------- //
 // tables (per CTA, in shared memory)
 // --------------------------------------------------------------------------- //
-template <class P> B2S_HD void build_tables(cfloat* smem, int q, int tid, int nthreads) {
+template <class P> B2S_HD void build_tables(cfloat* smem, int tid, int nthreads) {
   using D = Derived<P>;
   for (int n = tid; n < P::W; n += nthreads) smem[D::TW_OFF + n] = twiddle(n, P::W);
-  for (int e = tid; e < P::G * 4; e += nthreads) {
-    const int g = e >> 2, r = e & 3;
+  for (int e = tid; e < 2 * P::G * 4; e += nthreads) {
+    const int q = e / (P::G * 4), g = (e >> 2) % P::G, r = e & 3;
     cfloat t = twiddle(g * m_of<P>(r, q), P::H);
     if (g & 1) { t.x = -t.x; t.y = -t.y; }                      // (-1)^g of the input checkerboard
     smem[D::TH_OFF + e] = t;
@@ -104,65 +109,73 @@ template <class P> B2S_HD void build_tables(cfloat* smem, int q, int tid, int nt
 template <class P, class Pro>
 B2S_HD void phase_a(const Pro& pro, const typename Pro::Ctx& ctx, cfloat* smem, int q, int task) {
   using D = Derived<P>;
-  constexpr int G = P::G, R = P::R, X0 = P::X0;
-  const int g = task / X0, x0 = task - g * X0;
+  constexpr int G = P::G, R = P::R, X0 = P::X0, NC = P::NC;
+  const int g = task / D::XP, x0 = (task - g * D::XP) * NC;
   const float h = 0.70710678118654752440f;
 
   float wrow[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) wrow[j] = pro.row_weight(ctx, g + G * j);
+  for (int j = 0; j < 8; ++j) wrow[j] = pro.row_weight(ctx, g, G * j);
+  const typename Pro::Ptr tp = pro.task_ptr(ctx, g * P::W + x0);   // everything else is a constant offset
 
-  float ur[4][R], ui[4][R];                 // [m-block r][column index i]
+  float ur[NC][4][R], ui[NC][4][R];         // [column][m-block r][column-group index i]
 #pragma unroll
   for (int i = 0; i < R; ++i) {
-    const int x = x0 + X0 * i;
-    float fr[4], fi[4];
+    float fr[NC][4], fi[NC][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float ar, ai, br, bi;
-      pro.load(ctx, g + G * j, x, wrow[j], ar, ai);
-      pro.load(ctx, g + G * (j + 4), x, wrow[j + 4], br, bi);
-      if (q == 0) {
-        fr[j] = ar + br; fi[j] = ai + bi;
-      } else {
-        const float dr = ar - br, di = ai - bi;
-        if (j == 0)      { fr[j] = dr;              fi[j] = di; }
-        else if (j == 1) { fr[j] = (dr + di) * h;   fi[j] = (di - dr) * h; }
-        else if (j == 2) { fr[j] = di;              fi[j] = -dr; }
-        else             { fr[j] = (di - dr) * h;   fi[j] = -(dr + di) * h; }
+      float ar[NC], ai[NC], br[NC], bi[NC];
+      pro.template load<NC>(tp, (G * j) * P::W + X0 * i, wrow[j], ar, ai);
+      pro.template load<NC>(tp, (G * (j + 4)) * P::W + X0 * i, wrow[j + 4], br, bi);
+#pragma unroll
+      for (int n = 0; n < NC; ++n) {
+        if (q == 0) {
+          fr[n][j] = ar[n] + br[n]; fi[n][j] = ai[n] + bi[n];
+        } else {
+          const float dr = ar[n] - br[n], di = ai[n] - bi[n];
+          if (j == 0)      { fr[n][j] = dr;              fi[n][j] = di; }
+          else if (j == 1) { fr[n][j] = (dr + di) * h;   fi[n][j] = (di - dr) * h; }
+          else if (j == 2) { fr[n][j] = di;              fi[n][j] = -dr; }
+          else             { fr[n][j] = (di - dr) * h;   fi[n][j] = -(dr + di) * h; }
+        }
       }
     }
-    dft4(fr, fi);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) { ur[r][i] = fr[r]; ui[r][i] = fi[r]; }
+    for (int n = 0; n < NC; ++n) {
+      dft4(fr[n], fi[n]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { ur[n][r][i] = fr[n][r]; ui[n][r][i] = fi[n][r]; }
+    }
   }
-  // row twiddles (-1)^g w_H^{g m(r)}, times the column-parity sign (-1)^{x0}
-  const float sx = (x0 & 1) ? -1.f : 1.f;
+  // row twiddles (-1)^g w_H^{g m(r)}; the column-parity sign (-1)^{x} is applied per column below
   cfloat th[4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    th[r] = smem[D::TH_OFF + g * 4 + r];
-    th[r].x *= sx; th[r].y *= sx;
-  }
-  cfloat tw[R];
-#pragma unroll
-  for (int k1 = 1; k1 < R; ++k1) tw[k1] = smem[D::TW_OFF + (x0 * k1) % P::W];
+  for (int r = 0; r < 4; ++r) th[r] = smem[D::TH_OFF + (q * G + g) * 4 + r];
 
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int n = 0; n < NC; ++n) {
+    const int x = x0 + n;
+    const float sx = (x & 1) ? -1.f : 1.f;
+    cfloat tw[R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-      const float a = ur[r][i], b = ui[r][i];
-      ur[r][i] = a * th[r].x - b * th[r].y;
-      ui[r][i] = a * th[r].y + b * th[r].x;
-    }
-    Dft<R>::run(ur[r], ui[r]);
-    cfloat* dst = smem + (r * G + g) * P::PITCH + x0;
-    dst[0] = make_c(ur[r][0], ui[r][0]);
+    for (int k1 = 1; k1 < R; ++k1) tw[k1] = smem[D::TW_OFF + (x * k1) % P::W];
 #pragma unroll
-    for (int k1 = 1; k1 < R; ++k1) {
-      const float a = ur[r][k1], b = ui[r][k1];
-      dst[k1 * P::SEG] = make_c(a * tw[k1].x - b * tw[k1].y, a * tw[k1].y + b * tw[k1].x);
+    for (int r = 0; r < 4; ++r) {
+      const float tx = th[r].x * sx, ty = th[r].y * sx;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const float a = ur[n][r][i], b = ui[n][r][i];
+        ur[n][r][i] = a * tx - b * ty;
+        ui[n][r][i] = a * ty + b * tx;
+      }
+      Dft<R>::run(ur[n][r], ui[n][r]);
+      cfloat* dst = smem + (r * G + g) * P::PITCH + x;
+      dst[0] = make_c(ur[n][r][0], ui[n][r][0]);
+#pragma unroll
+      for (int k1 = 1; k1 < R; ++k1) {
+        const float a = ur[n][r][k1], b = ui[n][r][k1];
+        dst[k1 * P::SEG] = make_c(a * tw[k1].x - b * tw[k1].y, a * tw[k1].y + b * tw[k1].x);
+      }
     }
   }
 }
@@ -197,19 +210,29 @@ template <class P> B2S_HD void phase_b_write(cfloat* smem, const PhaseBRegs<P>& 
 template <class P, class Epi>
 B2S_HD void phase_c(const Epi& epi, const typename Epi::Ctx& ctx, const cfloat* smem, int q, int task,
                     float scale) {
-  constexpr int G = P::G;
-  const int r = task / P::W, kx = task - r * P::W;
+  using D = Derived<P>;
+  constexpr int G = P::G, NC = P::NC;
+  const int r = task / D::KXP, kx = (task - r * D::KXP) * NC;
   const int m = m_of<P>(r, q);
-  typename Epi::template Pre<G> pre;
-  epi.template prefetch<G>(ctx, m, kx, pre);          // rows m + 8*k, k = 0..G-1
-  float ur[G], ui[G];
-  const cfloat* src = smem + (r * G) * P::PITCH + kx;
+  const typename Epi::Ptr tp = epi.task_ptr(ctx, m, kx);   // rows m + 8*k: constant offsets 8*k*W
+  float ur[NC][G], ui[NC][G];
 #pragma unroll
-  for (int g = 0; g < G; ++g) { const cfloat v = src[g * P::PITCH]; ur[g] = v.x; ui[g] = v.y; }
-  Dft<G>::run(ur, ui);
-  const float s = ((q + kx) & 1) ? -scale : scale;    // (-1)^(ky+kx), ky = q mod 2
+  for (int n = 0; n < NC; ++n) {
+    const cfloat* src = smem + (r * G) * P::PITCH + kx + n;
 #pragma unroll
-  for (int k = 0; k < G; ++k) epi.template store<G>(ctx, m + 8 * k, kx, ur[k] * s, ui[k] * s, pre, k);
+    for (int g = 0; g < G; ++g) { const cfloat v = src[g * P::PITCH]; ur[n][g] = v.x; ui[n][g] = v.y; }
+    Dft<G>::run(ur[n], ui[n]);
+  }
+#pragma unroll
+  for (int k = 0; k < G; ++k) {
+    float re[NC], im[NC];
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+      const float s = ((q + kx + n) & 1) ? -scale : scale;    // (-1)^(ky+kx), ky = q mod 2
+      re[n] = ur[n][k] * s; im[n] = ui[n][k] * s;
+    }
+    epi.template store<NC>(tp, k, re, im);
+  }
 }
 
 // global sign (-1)^(H/2 + W/2) of the centred transform for even sizes

@@ -11,52 +11,87 @@
 //              EpiReduce   out[o] += conj(mult[m]) * y         (coil sum varnet.py:192-194, or the
 //                                                               frame sum of the sens-map gradient)
 //
-// "image" = linear index ((b*T + t)*C + c) of one H x W coil image.
+// "image" = linear index ((b*T + t)*C + c) of one H x W coil image.  Every
+// functor hands the core ONE pointer set per task (`task_ptr`); all further
+// addressing is compile-time constant offsets, so loads/stores carry immediates.
+// `load<NC>` / `store<NC>` move NC adjacent complex values with one 8*NC-byte access.
+// `l2_prefetch` issues bulk L2 prefetches for data a later phase / work item reads.
 #pragma once
 #include "fft2_core.cuh"
 
 namespace b2s {
 
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ void red_add2(cfloat* p, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+template <int NC> __device__ __forceinline__ void red_add(cfloat* p, const float* re, const float* im);
+template <> __device__ __forceinline__ void red_add<1>(cfloat* p, const float* re, const float* im) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(re[0]), "f"(im[0]) : "memory");
+}
+template <> __device__ __forceinline__ void red_add<2>(cfloat* p, const float* re, const float* im) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(re[0]), "f"(im[0]), "f"(re[1]), "f"(im[1]) : "memory");
+}
+// one instruction prefetches `bytes` (multiple of 16) contiguous bytes into L2
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 #else
-inline void red_add2(cfloat* p, float a, float b) { p->x += a; p->y += b; }
+template <int NC> inline void red_add(cfloat* p, const float* re, const float* im) {
+  for (int n = 0; n < NC; ++n) { p[n].x += re[n]; p[n].y += im[n]; }
+}
+inline void l2_prefetch_bulk(const void*, unsigned) {}
 #endif
 
-struct NoPre {};
+template <int NC> B2S_HD cvec<NC> ldv(const cfloat* p) { return *reinterpret_cast<const cvec<NC>*>(p); }
+template <int NC> B2S_HD void stv(cfloat* p, const cvec<NC>& v) { *reinterpret_cast<cvec<NC>*>(p) = v; }
+
+// `bytes` contiguous bytes in chunks of 32 KB, one chunk per thread
+B2S_HD void prefetch_span(const void* base, long long bytes, int tid) {
+  const long long chunk = 32768;
+  const long long off = (long long)tid * chunk;
+  if (off < bytes) l2_prefetch_bulk((const char*)base + off, (unsigned)((bytes - off) < chunk ? (bytes - off) : chunk));
+}
 
 // ------------------------------ prologues ---------------------------------- //
-template <int W, bool INV> struct ProPlain {
+template <int H, int W, bool INV> struct ProPlain {
   const cfloat* in; long long image_stride;
   struct Ctx { const cfloat* p; };
+  typedef const cfloat* Ptr;
   B2S_HD Ctx ctx(long long image) const { Ctx c; c.p = in + image * image_stride; return c; }
-  B2S_HD float row_weight(const Ctx&, int) const { return 1.f; }
-  B2S_HD void load(const Ctx& c, int y, int x, float, float& re, float& im) const {
-    const cfloat v = c.p[y * W + x];
-    re = INV ? v.y : v.x; im = INV ? v.x : v.y;
+  B2S_HD float row_weight(const Ctx&, int, int) const { return 1.f; }
+  B2S_HD Ptr task_ptr(const Ctx& c, int off) const { return c.p + off; }
+  template <int NC> B2S_HD void load(Ptr p, int off, float, float* re, float* im) const {
+    const cvec<NC> v = ldv<NC>(p + off);
+#pragma unroll
+    for (int n = 0; n < NC; ++n) { re[n] = INV ? v.v[n].y : v.v[n].x; im[n] = INV ? v.v[n].x : v.v[n].y; }
   }
+  B2S_HD void l2_prefetch(long long image, int tid) const { prefetch_span(in + image * image_stride, (long long)H * W * 8, tid); }
 };
 
-template <int W> struct ProExpand {
+template <int H, int W> struct ProExpand {
   const cfloat* img; const cfloat* sens; int T, C; long long hw;
   struct Ctx { const cfloat* a; const cfloat* s; };
+  struct Ptr { const cfloat* a; const cfloat* s; };
   B2S_HD Ctx ctx(long long image) const {
     const long long c = image % C, bt = image / C, b = bt / T;
     Ctx k; k.a = img + bt * hw; k.s = sens + (b * C + c) * hw; return k;
   }
-  B2S_HD float row_weight(const Ctx&, int) const { return 1.f; }
-  B2S_HD void load(const Ctx& c, int y, int x, float, float& re, float& im) const {
-    const cfloat a = c.a[y * W + x], s = c.s[y * W + x];
-    re = a.x * s.x - a.y * s.y; im = a.x * s.y + a.y * s.x;
+  B2S_HD float row_weight(const Ctx&, int, int) const { return 1.f; }
+  B2S_HD Ptr task_ptr(const Ctx& c, int off) const { Ptr p; p.a = c.a + off; p.s = c.s + off; return p; }
+  template <int NC> B2S_HD void load(const Ptr& p, int off, float, float* re, float* im) const {
+    const cvec<NC> a = ldv<NC>(p.a + off), s = ldv<NC>(p.s + off);
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+      re[n] = a.v[n].x * s.v[n].x - a.v[n].y * s.v[n].y;
+      im[n] = a.v[n].x * s.v[n].y + a.v[n].y * s.v[n].x;
+    }
   }
+  B2S_HD void l2_prefetch(long long, int) const {}             // image and maps are L2 resident
 };
 
 // WMODE 0: w = 1 ; 1: w = mask[ky] ; 2: w = 1 - eta*mask[ky], eta = v/(1+v), v read from device memory
-template <int W, int WMODE> struct ProKspace {
-  const cfloat* k; const uint8_t* mask; const float* vptr; int C, H; long long hw;
+template <int H, int W, int WMODE> struct ProKspace {
+  const cfloat* k; const uint8_t* mask; const float* vptr; int C; long long hw;
   struct Ctx { const cfloat* p; const uint8_t* m; float wa, wb; };
+  typedef const cfloat* Ptr;
   B2S_HD Ctx ctx(long long image) const {
     Ctx c; c.p = k + image * hw; c.m = WMODE ? mask + (image / C) * H : nullptr;
     c.wa = 1.f; c.wb = 0.f;
@@ -64,33 +99,41 @@ template <int W, int WMODE> struct ProKspace {
     if (WMODE == 2) { const float v = *vptr; c.wb = -v / (1.f + v); }
     return c;
   }
-  B2S_HD float row_weight(const Ctx& c, int y) const {
-    return WMODE ? c.wa + c.wb * (float)c.m[y] : 1.f;
+  B2S_HD float row_weight(const Ctx& c, int g, int off) const {
+    return WMODE ? c.wa + c.wb * (float)c.m[g + off] : 1.f;
   }
-  B2S_HD void load(const Ctx& c, int y, int x, float w, float& re, float& im) const {
-    const cfloat v = c.p[y * W + x];                 // inverse transform: feed swapped
-    if (WMODE) { re = v.y * w; im = v.x * w; } else { re = v.y; im = v.x; }
+  B2S_HD Ptr task_ptr(const Ctx& c, int off) const { return c.p + off; }
+  template <int NC> B2S_HD void load(Ptr p, int off, float w, float* re, float* im) const {
+    const cvec<NC> v = ldv<NC>(p + off);                  // inverse transform: feed swapped
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+      if (WMODE) { re[n] = v.v[n].y * w; im[n] = v.v[n].x * w; } else { re[n] = v.v[n].y; im[n] = v.v[n].x; }
+    }
   }
+  B2S_HD void l2_prefetch(long long image, int tid) const { prefetch_span(k + image * hw, (long long)H * W * 8, tid); }
 };
 
 // ------------------------------ epilogues ---------------------------------- //
-template <int W, bool INV> struct EpiPlain {
+template <int H, int W, bool INV> struct EpiPlain {
   cfloat* out; long long image_stride;
   struct Ctx { cfloat* p; };
-  template <int G> using Pre = NoPre;
+  typedef cfloat* Ptr;
   B2S_HD Ctx ctx(long long image) const { Ctx c; c.p = out + image * image_stride; return c; }
-  template <int G> B2S_HD void prefetch(const Ctx&, int, int, NoPre&) const {}
-  template <int G> B2S_HD void store(const Ctx& c, int ky, int kx, float re, float im, const NoPre&, int) const {
-    c.p[ky * W + kx] = INV ? make_c(im, re) : make_c(re, im);
+  B2S_HD Ptr task_ptr(const Ctx& c, int m, int kx) const { return c.p + m * W + kx; }
+  template <int NC> B2S_HD void store(Ptr p, int k, const float* re, const float* im) const {
+    cvec<NC> v;
+#pragma unroll
+    for (int n = 0; n < NC; ++n) v.v[n] = INV ? make_c(im[n], re[n]) : make_c(re[n], im[n]);
+    stv<NC>(p + 8 * k * W, v);
   }
+  B2S_HD void l2_prefetch(long long, int, int) const {}
 };
 
 // MODE 0: k ; 1: k*m + 0.0 ; 2: (1-m) k + m (k + v ref)/(1+v) ; 3: k*m - ref
-template <int W, int MODE> struct EpiKspace {
-  cfloat* out; const cfloat* ref; const uint8_t* mask; const float* vptr; int C, H; long long hw;
+template <int H, int W, int MODE> struct EpiKspace {
+  cfloat* out; const cfloat* ref; const uint8_t* mask; const float* vptr; int C; long long hw;
   struct Ctx { cfloat* p; const cfloat* r; const uint8_t* m; float v; };
-  template <int G> struct PreT { cfloat r[(MODE >= 2) ? G : 1]; uint8_t m[(MODE >= 1) ? G : 1]; };
-  template <int G> using Pre = PreT<G>;
+  struct Ptr { cfloat* p; const cfloat* r; const uint8_t* m; float v; };
   B2S_HD Ctx ctx(long long image) const {
     Ctx c; c.p = out + image * hw;
     c.r = (MODE >= 2) ? ref + image * hw : nullptr;
@@ -98,54 +141,65 @@ template <int W, int MODE> struct EpiKspace {
     c.v = (MODE == 2) ? *vptr : 0.f;
     return c;
   }
-  template <int G> B2S_HD void prefetch(const Ctx& c, int m0, int kx, PreT<G>& pre) const {
-    if (MODE >= 1) {
-#pragma unroll
-      for (int k = 0; k < G; ++k) pre.m[k] = c.m[m0 + 8 * k];
-    }
-    if (MODE >= 2) {
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        // DC only needs ref on sampled rows; the residual needs it everywhere
-        if (MODE == 3 || pre.m[k]) pre.r[k] = c.r[(m0 + 8 * k) * W + kx];
-        else pre.r[k] = make_c(0.f, 0.f);
-      }
-    }
+  B2S_HD Ptr task_ptr(const Ctx& c, int m, int kx) const {
+    Ptr t; const int off = m * W + kx;
+    t.p = c.p + off; t.r = (MODE >= 2) ? c.r + off : nullptr; t.m = (MODE >= 1) ? c.m + m : nullptr; t.v = c.v;
+    return t;
   }
-  template <int G> B2S_HD void store(const Ctx& c, int ky, int kx, float re, float im, const PreT<G>& pre, int k) const {
-    if (MODE == 1) { if (!pre.m[k]) { re = 0.f; im = 0.f; } }
-    if (MODE == 2) {
-      if (pre.m[k]) { re = (re + c.v * pre.r[k].x) / (1.f + c.v); im = (im + c.v * pre.r[k].y) / (1.f + c.v); }
+  template <int NC> B2S_HD void store(const Ptr& t, int k, const float* re_in, const float* im_in) const {
+    const bool mk = (MODE >= 1) ? (t.m[8 * k] != 0) : true;
+    cvec<NC> o;
+    if (MODE <= 1) {
+#pragma unroll
+      for (int n = 0; n < NC; ++n) o.v[n] = mk ? make_c(re_in[n], im_in[n]) : make_c(0.f, 0.f);
+    } else if (MODE == 2) {
+      if (mk) {                                             // ref is only needed on sampled rows
+        const cvec<NC> r = ldv<NC>(t.r + 8 * k * W);
+#pragma unroll
+        for (int n = 0; n < NC; ++n)
+          o.v[n] = make_c((re_in[n] + t.v * r.v[n].x) / (1.f + t.v), (im_in[n] + t.v * r.v[n].y) / (1.f + t.v));
+      } else {
+#pragma unroll
+        for (int n = 0; n < NC; ++n) o.v[n] = make_c(re_in[n], im_in[n]);
+      }
+    } else {
+      const cvec<NC> r = ldv<NC>(t.r + 8 * k * W);
+#pragma unroll
+      for (int n = 0; n < NC; ++n)
+        o.v[n] = mk ? make_c(re_in[n] - r.v[n].x, im_in[n] - r.v[n].y) : make_c(0.f - r.v[n].x, 0.f - r.v[n].y);
     }
-    if (MODE == 3) {
-      if (!pre.m[k]) { re = 0.f; im = 0.f; }
-      re -= pre.r[k].x; im -= pre.r[k].y;
-    }
-    c.p[ky * W + kx] = make_c(re, im);
+    stv<NC>(t.p + 8 * k * W, o);
+  }
+  // the reference k-space this item will blend with (whole image: the sibling half needs the rest)
+  B2S_HD void l2_prefetch(long long image, int q, int tid) const {
+    if (MODE >= 2 && q == 0) prefetch_span(ref + image * hw, (long long)H * W * 8, tid);
   }
 };
 
 // out[(b,t,c) . ostride] += conj(mult[(b,t,c) . mstride]) * ifft(k);  zero stride = reduced dim
-template <int W> struct EpiReduce {
+template <int H, int W> struct EpiReduce {
   cfloat* out; const cfloat* mult; int T, C;
   long long os_b, os_t, os_c, ms_b, ms_t, ms_c;
   struct Ctx { cfloat* o; const cfloat* m; };
-  template <int G> struct PreT { cfloat s[G]; };
-  template <int G> using Pre = PreT<G>;
+  struct Ptr { cfloat* o; const cfloat* m; };
   B2S_HD Ctx ctx(long long image) const {
     const long long c = image % C, bt = image / C, b = bt / T, t = bt % T;
     Ctx k; k.o = out + b * os_b + t * os_t + c * os_c; k.m = mult + b * ms_b + t * ms_t + c * ms_c;
     return k;
   }
-  template <int G> B2S_HD void prefetch(const Ctx& c, int m0, int kx, PreT<G>& pre) const {
+  B2S_HD Ptr task_ptr(const Ctx& c, int m, int kx) const { Ptr t; t.o = c.o + m * W + kx; t.m = c.m + m * W + kx; return t; }
+  template <int NC> B2S_HD void store(const Ptr& t, int k, const float* re, const float* im) const {
+    const cvec<NC> s = ldv<NC>(t.m + 8 * k * W);
+    float ar[NC], ai[NC];
 #pragma unroll
-    for (int k = 0; k < G; ++k) pre.s[k] = c.m[(m0 + 8 * k) * W + kx];
+    for (int n = 0; n < NC; ++n) {
+      const float yr = im[n], yi = re[n];                  // swap back (inverse transform)
+      ar[n] = yr * s.v[n].x + yi * s.v[n].y;
+      ai[n] = yi * s.v[n].x - yr * s.v[n].y;
+    }
+    red_add<NC>(t.o + 8 * k * W, ar, ai);
   }
-  template <int G> B2S_HD void store(const Ctx& c, int ky, int kx, float re, float im, const PreT<G>& pre, int k) const {
-    const float yr = im, yi = re;                      // swap back (inverse transform)
-    const cfloat s = pre.s[k];
-    red_add2(c.o + ky * W + kx, yr * s.x + yi * s.y, yi * s.x - yr * s.y);
-  }
+  B2S_HD void l2_prefetch(long long, int, int) const {}
 };
 
 }  // namespace b2s

@@ -6,7 +6,8 @@
 #include "fft2_kernel.cuh"
 
 using namespace b2s;
-typedef Plan<200, 200> P200;
+typedef Plan<200, 200, 256, 1> P200;
+typedef Plan<200, 200, 256, 2> P200V;   // the 128-bit variant is emulated too
 
 static float norm_scale(int h, int w, int inverse, int norm) {
   // norm: 0 "backward", 1 "ortho", 2 "forward" (torch.fft semantics)
@@ -24,12 +25,12 @@ int emu_fft2c(const float* in, float* out, long long n_images, int h, int w, int
   const float scale = norm_scale(h, w, inverse, norm) * centre_sign<P200>();
   const long long hw = (long long)h * w;
   if (inverse) {
-    ProPlain<200, true> pro{(const cfloat*)in, hw};
-    EpiPlain<200, true> epi{(cfloat*)out, hw};
+    ProPlain<200, 200, true> pro{(const cfloat*)in, hw};
+    EpiPlain<200, 200, true> epi{(cfloat*)out, hw};
     fft2_half_emulate<P200>(pro, epi, scale, n_images);
   } else {
-    ProPlain<200, false> pro{(const cfloat*)in, hw};
-    EpiPlain<200, false> epi{(cfloat*)out, hw};
+    ProPlain<200, 200, false> pro{(const cfloat*)in, hw};
+    EpiPlain<200, 200, false> epi{(cfloat*)out, hw};
     fft2_half_emulate<P200>(pro, epi, scale, n_images);
   }
   return 0;
@@ -40,8 +41,8 @@ int emu_sens_expand(const float* img, const float* sens, float* kout, const floa
   if (h != 200 || w != 200) return 2;
   const float scale = norm_scale(h, w, 0, norm) * centre_sign<P200>();
   const long long hw = (long long)h * w, n = (long long)b * t * c;
-  ProExpand<200> pro{(const cfloat*)img, (const cfloat*)sens, t, c, hw};
-#define RUN(M) { EpiKspace<200, M> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, h, hw}; \
+  ProExpand<200, 200> pro{(const cfloat*)img, (const cfloat*)sens, t, c, hw};
+#define RUN(M) { EpiKspace<200, 200, M> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, hw}; \
                  fft2_half_emulate<P200>(pro, epi, scale, n); }
   if (mode == 0) RUN(0) else if (mode == 1) RUN(1) else if (mode == 2) RUN(2) else if (mode == 3) RUN(3) else return 1;
 #undef RUN
@@ -53,7 +54,7 @@ int emu_sens_reduce(const float* k, const float* mult, float* out, const uint8_t
   if (h != 200 || w != 200) return 2;
   const float scale = norm_scale(h, w, 1, norm) * centre_sign<P200>();
   const long long hw = (long long)h * w, n = (long long)b * t * c;
-  EpiReduce<200> epi;
+  EpiReduce<200, 200> epi;
   epi.out = (cfloat*)out; epi.mult = (const cfloat*)mult; epi.T = t; epi.C = c;
   if (!over_frames) {   // out (b,t,h,w) = sum_c conj(S[b,c]) y[b,t,c]
     epi.os_b = t * hw; epi.os_t = hw; epi.os_c = 0; epi.ms_b = c * hw; epi.ms_t = 0; epi.ms_c = hw;
@@ -62,7 +63,7 @@ int emu_sens_reduce(const float* k, const float* mult, float* out, const uint8_t
     epi.os_b = c * hw; epi.os_t = 0; epi.os_c = hw; epi.ms_b = t * hw; epi.ms_t = hw; epi.ms_c = 0;
     for (long long i = 0; i < (long long)b * c * hw * 2; ++i) out[i] = 0.f;
   }
-#define RUN(M) { ProKspace<200, M> pro{(const cfloat*)k, mask, v, c, h, hw}; fft2_half_emulate<P200>(pro, epi, scale, n); }
+#define RUN(M) { ProKspace<200, 200, M> pro{(const cfloat*)k, mask, v, c, hw}; fft2_half_emulate<P200>(pro, epi, scale, n); }
   if (wmode == 0) RUN(0) else if (wmode == 1) RUN(1) else if (wmode == 2) RUN(2) else return 1;
 #undef RUN
   return 0;
