@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the SENSE / data-consistency hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Step      one pass of the hot path of a 12-cascade XF-VarNet forward (BASELINE.json configs[1]:
+          SensitivityModel pre/post, 12 x [A^H -> temporal head/tail -> A fused with the soft-DC
+          blend], final |A^H k|; regularisers = identity, they are outside the hot path) over a
+          batch of synthetic cine slices resident in HBM.
+value     cine slices / s, whole job (all ranks), device-timed with CUDA events, max over ranks.
+e2e       the same metric through the public API with HOST (pinned) buffers: H2D of every slice's
+          k-space + mask and D2H of the reconstructed cine inside the timed region.
+roofline  dominant kernel = the fused sens_expand + soft-DC kernel; algorithmic bytes I + S + 2K per
+          launch over its CUDA-event duration measured inside the timed region, vs MEASURED_PEAKS.json.
+cpu_baseline / --impl reference   the torch-CPU port of the reference's op chain (oracle/torch_port.py)
+          timed on the host cores on a bounded sample (one slice per step).
+Prints exactly ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = "XF-VarNet 12-cascade SENSE/DC hot path, 10-coil 15-frame 200x200 cine slices"
+CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=4)
+METRIC, UNIT = "cine_slices_per_sec", "slices/s"
+
+
+# --------------------------------------------------------------------------- #
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    p = ROOT / "profiles" / "r1_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("sens_expand_dc_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """SM clock and throttle reasons polled through NVML every 5 ms DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.sm, self.reasons, self.max_mhz, self._stop, self._th = index, [], set(), None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:                                   # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = get_reasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._th = threading.Thread(target=self._loop, daemon=True)
+            self._th.start()
+
+    def stop(self):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self._stop = True
+        self._th.join(timeout=1.0)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# --------------------------------------------------------------------------- #
+def make_inputs(rank: int, n_slices: int):
+    """Synthetic slices with the reference's conventions (deep_cine_cardiac_mri_b200/synth.py)."""
+    import numpy as np
+    from deep_cine_cardiac_mri_b200 import synth
+    cases = [synth.cine_case(1000 * rank + i, 1, CFG["t"], CFG["c"], CFG["h"], CFG["w"]) for i in range(n_slices)]
+    mk = np.concatenate([c["masked_kspace"] for c in cases], 0)
+    mask = np.concatenate([c["mask"] for c in cases], 0)
+    return mk, mask
+
+
+def cpu_reference_run(steps: int, warmup: int):
+    """torch-CPU port of the reference path on one slice per step; returns (slices/s, cores, sample)."""
+    import torch
+    from oracle import torch_port as T
+    mk, mask = make_inputs(0, 1)
+    mk, mask = torch.from_numpy(mk), torch.from_numpy(mask)
+    cores = torch.get_num_threads()
+    with torch.no_grad():
+        for _ in range(warmup):
+            T.varnet_hot_path(mk, mask, CFG["cascades"], 1.0)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            T.varnet_hot_path(mk, mask, CFG["cascades"], 1.0)
+        dt = time.perf_counter() - t0
+    return steps / dt, dt / steps, cores, f"{steps} x 1 slice (b=1) of the same workload, torch {torch.__version__} CPU, {cores} threads of {os.cpu_count()} cpus"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+    val, sec, cores, sample = cpu_reference_run(steps, warmup)
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, **CFG, "slices_per_step": 1, "note": "bounded sample: one slice per step on host cores"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------- #
+def run_ours(args, rank, world, local):
+    import torch
+    from deep_cine_cardiac_mri_b200 import _lib, ops, pipeline, dist as bdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the b200sense operators have no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.lib()
+    nb, K, W = CFG["slices_per_gpu_step"], args.steps, args.warmup
+    mk_np, mask_np = make_inputs(rank, nb)
+    mk_host = torch.from_numpy(mk_np).pin_memory()
+    mask_host = torch.from_numpy(mask_np).pin_memory()
+    mk, mask = mk_host.to(dev), mask_host.to(dev)
+    v = torch.ones(1, device=dev)
+    b, t, c, h, w = nb, CFG["t"], CFG["c"], CFG["h"], CFG["w"]
+    alg = pipeline.hot_path_algorithmic_bytes(b, t, c, h, w, CFG["cascades"])
+
+    # dominant-kernel timing: event pairs around every fused expand+DC launch of the timed region
+    dom_events = []
+    orig_expand = ops.raw_sens_expand
+
+    def timed_expand(*a, **kw):
+        if timed_expand.on and len(a) > 2 and a[2] == ops.EXPAND_DC:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); out = orig_expand(*a, **kw); e1.record()
+            dom_events.append((e0, e1))
+            return out
+        return orig_expand(*a, **kw)
+    timed_expand.on = False
+    ops.raw_sens_expand = timed_expand
+
+    def step():
+        return pipeline.varnet_hot_path(mk, mask, v, CFG["cascades"], xf=True)
+
+    with torch.no_grad():
+        for _ in range(W):
+            step()
+        torch.cuda.synchronize()
+        bdist.barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        lib.b2s_launch_count(1)
+        timed_expand.on = True
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(K):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        timed_expand.on = False
+        launches = int(lib.b2s_launch_count(0))
+        bdist.barrier()
+        sec = bdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+        clocks = sampler.stop() if rank == 0 else None
+        dom_ms = [a.elapsed_time(bb) for a, bb in dom_events]
+        dom_sec = (sum(dom_ms) / len(dom_ms)) * 1e-3 if dom_ms else float("nan")
+
+        # ---- e2e: pinned host buffers in, reconstructed cine out, copies inside the timed region ----
+        copy_stream, comp_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        bufs = [(torch.empty_like(mk), torch.empty_like(mask)) for _ in range(2)]
+        out_host = [torch.empty((b, t, h, w), dtype=torch.float32).pin_memory() for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_run(n):
+            for i in range(n):
+                s = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[s])
+                    bufs[s][0].copy_(mk_host, non_blocking=True)
+                    bufs[s][1].copy_(mask_host, non_blocking=True)
+                    ready[s].record(copy_stream)
+                with torch.cuda.stream(comp_stream):
+                    comp_stream.wait_event(ready[s])
+                    res = pipeline.varnet_hot_path(bufs[s][0], bufs[s][1], v, CFG["cascades"], xf=True)
+                    out_host[s].copy_(res, non_blocking=True)
+                    freed[s].record(comp_stream)
+            comp_stream.synchronize()
+
+        for s in range(2):
+            freed[s].record(comp_stream)
+        e2e_run(max(2, min(W, 3)))
+        torch.cuda.synchronize()
+        bdist.barrier()
+        t0 = time.perf_counter()
+        e2e_run(K)
+        torch.cuda.synchronize()
+        e2e_sec = bdist.max_over_ranks(time.perf_counter() - t0, dev)
+        bdist.barrier()
+
+    if rank != 0:
+        return
+    peak, peak_src = load_peaks()
+    achieved = alg["sens_expand_dc"] / dom_sec / 1e9
+    dc_step_gbs = None
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        val, s_per, cores, sample = cpu_reference_run(3, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    result = {
+        "metric": METRIC, "value": world * nb * K / sec, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, **CFG, "global_slices_per_step": world * nb, "parallelism": f"dp{world} (slices sharded, no collective)",
+                   "l2": f"inputs larger than L2: {alg['K'] / 1e6:.0f} MB k-space per tensor per step", "regulariser": "identity (outside the hot path)"},
+        "clocks": clocks,
+        "e2e": {"value": world * nb * K / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(mk_host.numel() * 4 + mask_host.numel()),
+                "d2h_bytes_per_step": int(b * t * h * w * 4)},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": load_traffic(), "kernel": "fft2_half_kernel<ProExpand, EpiKspace<DC>> (sens_expand + soft-DC)",
+                     "algorithmic_bytes_per_launch": alg["sens_expand_dc"], "us_per_launch": dom_sec * 1e6,
+                     "launches_timed": len(dom_ms), "peak_source": peak_src},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(result), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    from deep_cine_cardiac_mri_b200 import dist as bdist
+    rank, world, local = bdist.init_from_env()
+    try:
+        run_ours(args, rank, world, local)
+    finally:
+        import torch.distributed as td
+        if td.is_initialized():
+            td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

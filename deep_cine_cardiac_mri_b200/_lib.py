@@ -21,6 +21,7 @@ _p, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 SIGNATURES = {
     "b2s_version": [],
     "b2s_last_error": [],
+    "b2s_launch_count": [_i],
     "b2s_has_fused_plan": [_i, _i],
     "b2s_scratch_bytes": [_i, _i, _i, _i, _i],
     "b2s_fft2c": [_p, _p, _i64, _i, _i, _i, _i, _p],
@@ -46,7 +47,7 @@ SIGNATURES = {
     "b2s_dc_step_ws_bytes": [_i, _i, _i, _i, _i],
     "b2s_dc_step_host": [_p, _p, _p, _p, _f, _p, _i, _i, _i, _i, _i, _p, _sz, _p],
 }
-_RESTYPE = {"b2s_last_error": C.c_char_p, "b2s_scratch_bytes": _sz, "b2s_dc_step_ws_bytes": _sz}
+_RESTYPE = {"b2s_launch_count": C.c_ulonglong, "b2s_last_error": C.c_char_p, "b2s_scratch_bytes": _sz, "b2s_dc_step_ws_bytes": _sz}
 
 
 def build(verbose: bool = False) -> Path:

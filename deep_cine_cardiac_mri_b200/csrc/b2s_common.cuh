@@ -12,7 +12,10 @@ void set_error(const char* fmt, ...);          // defined in b2s_abi.cu (thread-
 
 inline int fail(int code, const char* what) { set_error("%s", what); return code; }
 
-inline int check_launch(const char* what) {
+extern unsigned long long g_kernel_launches;   // b2s_abi.cu; kernels launched through this library
+
+inline int check_launch(const char* what, int n_kernels = 1) {
+  g_kernel_launches += (unsigned long long)n_kernels;
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return B2S_ECUDA; }
   return B2S_OK;

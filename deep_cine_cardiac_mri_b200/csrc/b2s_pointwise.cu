@@ -478,7 +478,7 @@ extern "C" int b2s_dot(const float* a, const float* b, float* out, int64_t n, fl
   const unsigned g = grid_for(n, NT, 1024);
   dot_partial_kernel<<<g, NT, 0, (cudaStream_t)stream>>>(a, b, scratch, n);
   dot_final_kernel<<<1, NT, 0, (cudaStream_t)stream>>>(scratch, out, (int)g);
-  return check_launch("dot kernels");
+  return check_launch("dot kernels", 2);
 }
 
 extern "C" int b2s_axpy_ratio(float* y, const float* x, const float* num, const float* den, float sign, int64_t n, void* stream) {

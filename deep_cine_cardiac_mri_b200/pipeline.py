@@ -1,0 +1,59 @@
+"""Whole-slice SENSE/DC hot path of an unrolled XF/XT-VarNet forward on the fused kernels.
+
+This is the path `models/varnet.py:143-151` (VarNet.forward) walks between the
+regularisers: SensitivityModel pre/post, then per cascade A^H -> temporal head ->
+[regulariser] -> temporal tail -> A fused with the soft-DC blend, then |A^H k|.
+The regularisers are passed in as callables (the reference's cuDNN U-Nets, untouched);
+`None` means identity, which is what the hot-path benchmark measures.  No host
+synchronisation happens anywhere in here, so the whole call is CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence, Union
+
+import torch
+
+from . import ops
+from . import functional as F
+from . import blocks
+
+
+def sensitivity_maps(masked_kspace: torch.Tensor, mask: torch.Tensor,
+                     sens_unet: Optional[Callable] = None) -> torch.Tensor:
+    """(b,t,c,h,w,2), mask (b,t,1,h,1,1) -> (b,1,c,h,w,2)  (models/varnet.py:62-86)."""
+    x = blocks._sens_pre(masked_kspace, mask)
+    if sens_unet is not None:
+        x = sens_unet(x)
+    return ops.RssNormalizeFn.apply(x).unsqueeze(1)
+
+
+def varnet_hot_path(masked_kspace: torch.Tensor, mask: torch.Tensor,
+                    v: Union[float, torch.Tensor, Sequence] = 1.0, n_cascades: int = 12, xf: bool = True,
+                    regulariser: Optional[Callable] = None, sens_unet: Optional[Callable] = None,
+                    sens_maps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Returns the reconstructed magnitude cine (b,t,h,w)."""
+    b, t, c, h, w, _ = masked_kspace.shape
+    sens = sensitivity_maps(masked_kspace, mask, sens_unet) if sens_maps is None else sens_maps
+    m8 = ops._mask_u8(mask, b, t, h)
+    vs = list(v) if isinstance(v, (list, tuple)) else [v] * n_cascades
+    vs = [x if isinstance(x, torch.Tensor) else ops._vdev(x, masked_kspace.device) for x in vs]
+    k = masked_kspace
+    for i in range(n_cascades):
+        img = ops.sens_reduce(k, sens)                                   # A^H k            (b,t,h,w,2)
+        x, mean = ops.TemporalPreFn.apply(img, xf)                       # - mean_t, fft1c_t
+        if regulariser is not None:
+            x = regulariser(x.unsqueeze(2)).squeeze(2)
+        model_out = ops.TemporalPostFn.apply(x, mean, xf)                # ifft1c_t, + mean_t
+        k = ops.SensExpandFn.apply(model_out, sens.squeeze(1), masked_kspace, m8, vs[i], ops.EXPAND_DC, 1)
+    return F.complex_abs(ops.sens_reduce(k, sens))
+
+
+def hot_path_algorithmic_bytes(b: int, t: int, c: int, h: int, w: int, n_cascades: int) -> dict:
+    """Algorithmic HBM bytes of the calls above, fp32."""
+    K, I, S = b * t * c * h * w * 8, b * t * h * w * 8, b * c * h * w * 8
+    return {
+        "sens_reduce": K + S + I, "sens_expand_dc": I + S + 2 * K, "dc_step": 3 * K + 2 * I + 2 * S,
+        "temporal": 2 * (2 * I + I // t), "total": n_cascades * (3 * K + 2 * I + 2 * S + 2 * (2 * I + I // t))
+        + (K + S + I) + 2 * S + b * c * h * w * 8,
+        "K": K, "I": I, "S": S,
+    }

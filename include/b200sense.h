@@ -50,6 +50,8 @@ extern "C" {
 
 int b2s_version(void);
 const char* b2s_last_error(void);
+/* number of CUDA kernels this library has launched so far (host-side counter; reset != 0 zeroes it) */
+unsigned long long b2s_launch_count(int reset);
 /* 1 if (h,w) runs on the fused single-pass kernels, 0 if on the generic two-pass ones */
 int b2s_has_fused_plan(int h, int w);
 /* bytes of scratch b2s_sens_expand / b2s_sens_reduce need for this shape (0 for fused plans) */

@@ -35,9 +35,10 @@ def make_mask(seed, b, t, h, n_center=10, acc=4):
     rng = np.random.default_rng(seed)
     m = np.zeros((b, t, h), dtype=np.uint8)
     pdf = np.exp(-(0.5 / (h / 10.0) ** 2) * (np.arange(h) - h / 2) ** 2) + (h / (2.0 * acc)) / h
+    n_center = min(n_center, max(h // 4, 1))
     pdf[h // 2 - n_center // 2: h // 2 + n_center // 2] = 0
     pdf /= pdf.sum()
-    n_lines = int(h / acc) - n_center
+    n_lines = max(int(h / acc) - n_center, 0)
     for i in range(b):
         for j in range(t):
             m[i, j, rng.choice(h, n_lines, replace=False, p=pdf)] = 1

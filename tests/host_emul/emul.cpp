@@ -18,7 +18,12 @@ static float norm_scale(int h, int w, int inverse, int norm) {
   return (float)s;
 }
 
+static int g_variant = 0;   // 0: 64-bit accesses (NC=1), 1: 128-bit accesses (NC=2)
+#define EMU(PRO, EPI, SCALE, N) do { if (g_variant) fft2_half_emulate<P200V>(PRO, EPI, SCALE, N); else fft2_half_emulate<P200>(PRO, EPI, SCALE, N); } while (0)
+
 extern "C" {
+
+void emu_set_variant(int v) { g_variant = v; }
 
 int emu_fft2c(const float* in, float* out, long long n_images, int h, int w, int inverse, int norm) {
   if (h != 200 || w != 200) return 2;
@@ -27,11 +32,11 @@ int emu_fft2c(const float* in, float* out, long long n_images, int h, int w, int
   if (inverse) {
     ProPlain<200, 200, true> pro{(const cfloat*)in, hw};
     EpiPlain<200, 200, true> epi{(cfloat*)out, hw};
-    fft2_half_emulate<P200>(pro, epi, scale, n_images);
+    EMU(pro, epi, scale, n_images);
   } else {
     ProPlain<200, 200, false> pro{(const cfloat*)in, hw};
     EpiPlain<200, 200, false> epi{(cfloat*)out, hw};
-    fft2_half_emulate<P200>(pro, epi, scale, n_images);
+    EMU(pro, epi, scale, n_images);
   }
   return 0;
 }
@@ -43,7 +48,7 @@ int emu_sens_expand(const float* img, const float* sens, float* kout, const floa
   const long long hw = (long long)h * w, n = (long long)b * t * c;
   ProExpand<200, 200> pro{(const cfloat*)img, (const cfloat*)sens, t, c, hw};
 #define RUN(M) { EpiKspace<200, 200, M> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, hw}; \
-                 fft2_half_emulate<P200>(pro, epi, scale, n); }
+                 EMU(pro, epi, scale, n); }
   if (mode == 0) RUN(0) else if (mode == 1) RUN(1) else if (mode == 2) RUN(2) else if (mode == 3) RUN(3) else return 1;
 #undef RUN
   return 0;
@@ -63,7 +68,7 @@ int emu_sens_reduce(const float* k, const float* mult, float* out, const uint8_t
     epi.os_b = c * hw; epi.os_t = 0; epi.os_c = hw; epi.ms_b = t * hw; epi.ms_t = hw; epi.ms_c = 0;
     for (long long i = 0; i < (long long)b * c * hw * 2; ++i) out[i] = 0.f;
   }
-#define RUN(M) { ProKspace<200, 200, M> pro{(const cfloat*)k, mask, v, c, hw}; fft2_half_emulate<P200>(pro, epi, scale, n); }
+#define RUN(M) { ProKspace<200, 200, M> pro{(const cfloat*)k, mask, v, c, hw}; EMU(pro, epi, scale, n); }
   if (wmode == 0) RUN(0) else if (wmode == 1) RUN(1) else if (wmode == 2) RUN(2) else return 1;
 #undef RUN
   return 0;
