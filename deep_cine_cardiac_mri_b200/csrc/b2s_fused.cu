@@ -10,19 +10,12 @@ using namespace b2s;
 namespace {
 
 typedef Plan<200, 200, 256, 1> P200;    // 8 warps x 255 registers, 64-bit global accesses
-typedef Plan<200, 200, 512, 1> P200N;   // experimental: 16 warps x 128 registers, 64-bit accesses
 
-int plan_threads() {
-  static int nt = 0;
-  if (!nt) { const char* e = getenv("B2S_NT"); nt = (e && atoi(e) == 512) ? 512 : 256; }
-  return nt;
-}
-
-template <class P, class Pro, class Epi>
+template <class P, class Pro, class Epi, bool CARRY = false>
 int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st) {
   if (n_images <= 0) return B2S_OK;
   if (2 * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
-  auto kern = fft2_half_kernel<P, Pro, Epi>;
+  auto kern = fft2_half_kernel<P, Pro, Epi, CARRY>;
   int dev = 0, sms = 0;
   B2S_CUDA(cudaGetDevice(&dev));
   static int sm_count[64] = {0};             // immutable per-device facts
@@ -64,11 +57,11 @@ extern "C" int b2s_fft2c(const float* in, float* out, int64_t n_images, int h, i
     if (inverse) {
       ProPlain<200, 200, true> pro{(const cfloat*)in, hw};
       EpiPlain<200, 200, true> epi{(cfloat*)out, hw};
-      return (plan_threads() == 512) ? launch_fused<P200N>(pro, epi, s, n_images, st) : launch_fused<P200>(pro, epi, s, n_images, st);
+      return launch_fused<P200, ProPlain<200, 200, true>, EpiPlain<200, 200, true>, true>(pro, epi, s, n_images, st);
     }
     ProPlain<200, 200, false> pro{(const cfloat*)in, hw};
     EpiPlain<200, 200, false> epi{(cfloat*)out, hw};
-    return (plan_threads() == 512) ? launch_fused<P200N>(pro, epi, s, n_images, st) : launch_fused<P200>(pro, epi, s, n_images, st);
+    return launch_fused<P200, ProPlain<200, 200, false>, EpiPlain<200, 200, false>, true>(pro, epi, s, n_images, st);
   }
   return generic_fft2(in, out, n_images, h, w, inverse, scale, st);
 }
@@ -93,7 +86,7 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
 #define B2S_RUN(M)                                                                            \
   {                                                                                           \
     EpiKspace<200, 200, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};            \
-    return (plan_threads() == 512) ? launch_fused<P200N>(pro, epi, s, n, st) : launch_fused<P200>(pro, epi, s, n, st);                                          \
+    return launch_fused<P200>(pro, epi, s, n, st);                                          \
   }
     switch (mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) case 2: B2S_RUN(2) default: B2S_RUN(3) }
 #undef B2S_RUN
@@ -133,7 +126,7 @@ extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* ou
 #define B2S_RUN(M)                                                            \
   {                                                                           \
     ProKspace<200, 200, M> pro{(const cfloat*)kspace, mask, v, c, hw};          \
-    return (plan_threads() == 512) ? launch_fused<P200N>(pro, epi, s, n, st) : launch_fused<P200>(pro, epi, s, n, st);                          \
+    return launch_fused<P200>(pro, epi, s, n, st);                          \
   }
     switch (weight_mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) default: B2S_RUN(2) }
 #undef B2S_RUN

@@ -104,81 +104,117 @@ template <class P> B2S_HD void build_tables(cfloat* smem, int tid, int nthreads)
 }
 
 // --------------------------------------------------------------------------- //
-// Phase A
+// Phase A — software-pipelined over "steps".
+//
+// A thread owns TPT tasks (g, x0) per work item; a task is R steps (one step = the 8 rows
+// {g + G*j} of column group i).  The raw global loads of step s + QD are issued right after
+// step s has been consumed, into a register queue of QD slots that stays live across Phase B,
+// Phase C and the work-item boundary: global/L2 latency is hidden behind the register
+// codelets of all three phases instead of being exposed at the head of every Phase A
+// (shared memory is full, registers are the only landing zone).
 // --------------------------------------------------------------------------- //
-template <class P, class Pro>
-B2S_HD void phase_a(const Pro& pro, const typename Pro::Ctx& ctx, cfloat* smem, int q, int task) {
+template <class P, class Pro> struct PhaseA {
   using D = Derived<P>;
-  constexpr int G = P::G, R = P::R, X0 = P::X0, NC = P::NC;
-  const int g = task / D::XP, x0 = (task - g * D::XP) * NC;
-  const float h = 0.70710678118654752440f;
+  static constexpr int G = P::G, R = P::R, X0 = P::X0, NC = P::NC, NT = P::NT;
+  static constexpr int TPT = (D::TASKS_A + NT - 1) / NT;       // tasks per thread and item
+  static constexpr int STEPS = TPT * R;
+  static constexpr int QD = Pro::QDEPTH;                        // steps in flight
+  static_assert(STEPS % QD == 0, "queue depth must divide the steps of an item");
+  typedef typename Pro::template Unit<NC> Unit;
+  struct Queue { Unit u[QD]; };
 
-  float wrow[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) wrow[j] = pro.row_weight(ctx, g, G * j);
-  const typename Pro::Ptr tp = pro.task_ptr(ctx, g * P::W + x0);   // everything else is a constant offset
+  static B2S_HD bool task_of(int tid, int k, int& g, int& x0) {
+    const int task = tid + k * NT;
+    g = task / D::XP; x0 = (task - g * D::XP) * NC;
+    return task < D::TASKS_A;
+  }
 
-  float ur[NC][4][R], ui[NC][4][R];         // [column][m-block r][column-group index i]
+  // raw loads of step s (task s / R, column group s % R) of the item described by ctx
+  static B2S_HD void issue(const Pro& pro, const typename Pro::Ctx& ctx, int tid, int s, Unit& u) {
+    int g, x0;
+    if (!task_of(tid, s / R, g, x0)) return;
+    pro.template fetch<NC, G * P::W>(ctx, g, g * P::W + x0 + X0 * (s % R), u);
+  }
+
+  static B2S_HD void prefill(const Pro& pro, const typename Pro::Ctx& ctx, int tid, Queue& q) {
 #pragma unroll
-  for (int i = 0; i < R; ++i) {
-    float fr[NC][4], fi[NC][4];
+    for (int s = 0; s < QD; ++s) issue(pro, ctx, tid, s, q.u[s]);
+  }
+
+  // consume the queue for one work item (half q), refilling it from this item and then the next
+  static B2S_HD void run(const Pro& pro, const typename Pro::Ctx& ctx, const typename Pro::Ctx& next, bool has_next,
+                         cfloat* smem, int q, int tid, Queue& qu) {
+    const float h = 0.70710678118654752440f;
+    float ur[NC][4][R], ui[NC][4][R];       // [column][m-block r][column-group index i]
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float ar[NC], ai[NC], br[NC], bi[NC];
-      pro.template load<NC>(tp, (G * j) * P::W + X0 * i, wrow[j], ar, ai);
-      pro.template load<NC>(tp, (G * (j + 4)) * P::W + X0 * i, wrow[j + 4], br, bi);
+    for (int s = 0; s < STEPS; ++s) {
+      const int k = s / R, i = s % R, slot = s % QD;
+      int g, x0;
+      const bool valid = task_of(tid, k, g, x0);
+      // ---- consume step s: fold the row pairs (j, j+4), W8 twiddles, radix-4 over j
+      float fr[NC][4], fi[NC][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float ar[NC], ai[NC], br[NC], bi[NC];
+        pro.template value<NC>(qu.u[slot], j, ar, ai);
+        pro.template value<NC>(qu.u[slot], j + 4, br, bi);
+#pragma unroll
+        for (int n = 0; n < NC; ++n) {
+          if (q == 0) {
+            fr[n][j] = ar[n] + br[n]; fi[n][j] = ai[n] + bi[n];
+          } else {
+            const float dr = ar[n] - br[n], di = ai[n] - bi[n];
+            if (j == 0)      { fr[n][j] = dr;              fi[n][j] = di; }
+            else if (j == 1) { fr[n][j] = (dr + di) * h;   fi[n][j] = (di - dr) * h; }
+            else if (j == 2) { fr[n][j] = di;              fi[n][j] = -dr; }
+            else             { fr[n][j] = (di - dr) * h;   fi[n][j] = -(dr + di) * h; }
+          }
+        }
+      }
 #pragma unroll
       for (int n = 0; n < NC; ++n) {
-        if (q == 0) {
-          fr[n][j] = ar[n] + br[n]; fi[n][j] = ai[n] + bi[n];
-        } else {
-          const float dr = ar[n] - br[n], di = ai[n] - bi[n];
-          if (j == 0)      { fr[n][j] = dr;              fi[n][j] = di; }
-          else if (j == 1) { fr[n][j] = (dr + di) * h;   fi[n][j] = (di - dr) * h; }
-          else if (j == 2) { fr[n][j] = di;              fi[n][j] = -dr; }
-          else             { fr[n][j] = (di - dr) * h;   fi[n][j] = -(dr + di) * h; }
+        dft4(fr[n], fi[n]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { ur[n][r][i] = fr[n][r]; ui[n][r][i] = fi[n][r]; }
+      }
+      // ---- refill the slot with step s + QD (of this item, else of the next one)
+      if (s + QD < STEPS) issue(pro, ctx, tid, s + QD, qu.u[slot]);
+      else if (has_next) issue(pro, next, tid, s + QD - STEPS, qu.u[slot]);
+      // ---- last column group of the task: row twiddles, radix-R over i, column twiddles, store
+      if (i == R - 1 && valid) {
+        cfloat th[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) th[r] = smem[D::TH_OFF + (q * G + g) * 4 + r];
+#pragma unroll
+        for (int n = 0; n < NC; ++n) {
+          const int x = x0 + n;
+          const float sx = (x & 1) ? -1.f : 1.f;      // column parity of the input checkerboard
+          cfloat tw[R];
+#pragma unroll
+          for (int k1 = 1; k1 < R; ++k1) tw[k1] = smem[D::TW_OFF + (x * k1) % P::W];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float tx = th[r].x * sx, ty = th[r].y * sx;
+#pragma unroll
+            for (int ii = 0; ii < R; ++ii) {
+              const float a = ur[n][r][ii], b = ui[n][r][ii];
+              ur[n][r][ii] = a * tx - b * ty;
+              ui[n][r][ii] = a * ty + b * tx;
+            }
+            Dft<R>::run(ur[n][r], ui[n][r]);
+            cfloat* dst = smem + (r * G + g) * P::PITCH + x;
+            dst[0] = make_c(ur[n][r][0], ui[n][r][0]);
+#pragma unroll
+            for (int k1 = 1; k1 < R; ++k1) {
+              const float a = ur[n][r][k1], b = ui[n][r][k1];
+              dst[k1 * P::SEG] = make_c(a * tw[k1].x - b * tw[k1].y, a * tw[k1].y + b * tw[k1].x);
+            }
+          }
         }
       }
     }
-#pragma unroll
-    for (int n = 0; n < NC; ++n) {
-      dft4(fr[n], fi[n]);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) { ur[n][r][i] = fr[n][r]; ui[n][r][i] = fi[n][r]; }
-    }
   }
-  // row twiddles (-1)^g w_H^{g m(r)}; the column-parity sign (-1)^{x} is applied per column below
-  cfloat th[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) th[r] = smem[D::TH_OFF + (q * G + g) * 4 + r];
-
-#pragma unroll
-  for (int n = 0; n < NC; ++n) {
-    const int x = x0 + n;
-    const float sx = (x & 1) ? -1.f : 1.f;
-    cfloat tw[R];
-#pragma unroll
-    for (int k1 = 1; k1 < R; ++k1) tw[k1] = smem[D::TW_OFF + (x * k1) % P::W];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float tx = th[r].x * sx, ty = th[r].y * sx;
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const float a = ur[n][r][i], b = ui[n][r][i];
-        ur[n][r][i] = a * tx - b * ty;
-        ui[n][r][i] = a * ty + b * tx;
-      }
-      Dft<R>::run(ur[n][r], ui[n][r]);
-      cfloat* dst = smem + (r * G + g) * P::PITCH + x;
-      dst[0] = make_c(ur[n][r][0], ui[n][r][0]);
-#pragma unroll
-      for (int k1 = 1; k1 < R; ++k1) {
-        const float a = ur[n][r][k1], b = ui[n][r][k1];
-        dst[k1 * P::SEG] = make_c(a * tw[k1].x - b * tw[k1].y, a * tw[k1].y + b * tw[k1].x);
-      }
-    }
-  }
-}
+};
 
 // --------------------------------------------------------------------------- //
 // Phase B: read (segment layout) -> X0-point codelet ; write (natural layout)
@@ -215,6 +251,8 @@ B2S_HD void phase_c(const Epi& epi, const typename Epi::Ctx& ctx, const cfloat* 
   const int r = task / D::KXP, kx = (task - r * D::KXP) * NC;
   const int m = m_of<P>(r, q);
   const typename Epi::Ptr tp = epi.task_ptr(ctx, m, kx);   // rows m + 8*k: constant offsets 8*k*W
+  typename Epi::template Pre<G, NC> pre;
+  epi.template prefetch<G, NC>(tp, pre);                   // epilogue operands in flight behind the codelet
   float ur[NC][G], ui[NC][G];
 #pragma unroll
   for (int n = 0; n < NC; ++n) {
@@ -231,7 +269,7 @@ B2S_HD void phase_c(const Epi& epi, const typename Epi::Ctx& ctx, const cfloat* 
       const float s = ((q + kx + n) & 1) ? -scale : scale;    // (-1)^(ky+kx), ky = q mod 2
       re[n] = ur[n][k] * s; im[n] = ui[n][k] * s;
     }
-    epi.template store<NC>(tp, k, re, im);
+    epi.template store<G, NC>(tp, k, re, im, pre);
   }
 }
 

@@ -15,7 +15,10 @@ __device__ unsigned long long g_phase_cycles[8];
 #define B2S_TICK(slot) do { } while (0)
 #endif
 
-template <class P, class Pro, class Epi>
+// CARRY: keep the Phase A load queue alive across Phases B/C and the item boundary (hides the head
+// latency of every Phase A; costs QD*16 registers during Phase C, so only epilogues without operand
+// prefetch use it).
+template <class P, class Pro, class Epi, bool CARRY>
 __global__ void __launch_bounds__(P::NT, 1)
 fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_items, const unsigned stagger_ns) {
   using D = Derived<P>;
@@ -37,20 +40,23 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
 #ifdef B2S_PHASE_TIMING
   long long tprev = clock64();
 #endif
+  typedef PhaseA<P, Pro> PA;
+  typename PA::Queue queue;
+  if (CARRY && (int)blockIdx.x < n_items) PA::prefill(pro, pro.ctx(blockIdx.x >> 1), tid, queue);
+
 #pragma unroll 1
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const long long image = item >> 1;
     const int q = item & 1;
+    const int next = item + (int)gridDim.x;
+    const bool has_next = next < n_items;
     epi.l2_prefetch(image, q, tid);                        // what Phase C will read
-    {
-      const typename Pro::Ctx pctx = pro.ctx(image);
-      for (int task = tid; task < D::TASKS_A; task += P::NT) phase_a<P>(pro, pctx, smem, q, task);
-    }
+    if (!CARRY) PA::prefill(pro, pro.ctx(image), tid, queue);
+    PA::run(pro, pro.ctx(image), pro.ctx(has_next ? (next >> 1) : image), CARRY && has_next, smem, q, tid, queue);
     __syncthreads();
     B2S_TICK(0);
-
-    const int next = item + (int)gridDim.x;                // warm L2 with the next item's input
-    if (next < n_items && !(next & 1)) pro.l2_prefetch(next >> 1, tid);
+    // warm L2 with the rest of the next item while this SM is busy with register codelets (Phases B, C)
+    if (has_next && !(next & 1)) pro.l2_prefetch(next >> 1, tid);
 
 #pragma unroll 1
     for (int round = 0; round < D::ROUNDS_B; ++round) {
@@ -78,17 +84,21 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
 template <class P, class Pro, class Epi>
 void fft2_half_emulate(const Pro& pro, const Epi& epi, float scale, long long n_images) {
   using D = Derived<P>;
+  typedef PhaseA<P, Pro> PA;
   cfloat* smem = new cfloat[D::SMEM_ELEMS];
   PhaseBRegs<P>* regs = new PhaseBRegs<P>[P::NT];
+  typename PA::Queue* queues = new typename PA::Queue[P::NT];
   for (int i = 0; i < D::SMEM_ELEMS; ++i) smem[i] = make_c(0.f, 0.f);
   for (int tid = 0; tid < P::NT; ++tid) build_tables<P>(smem, tid, P::NT);
-  for (long long item = 0; item < 2 * n_images; ++item) {
+  const long long n_items = 2 * n_images;
+  if (n_items > 0) for (int tid = 0; tid < P::NT; ++tid) PA::prefill(pro, pro.ctx(0), tid, queues[tid]);
+  for (long long item = 0; item < n_items; ++item) {          // one "CTA" walks every item (gridDim = 1)
     const long long image = item >> 1;
     const int q = (int)(item & 1);
-    const typename Pro::Ctx pctx = pro.ctx(image);
+    const bool has_next = item + 1 < n_items;
     const typename Epi::Ctx ectx = epi.ctx(image);
     for (int tid = 0; tid < P::NT; ++tid)
-      for (int task = tid; task < D::TASKS_A; task += P::NT) phase_a<P>(pro, pctx, smem, q, task);
+      PA::run(pro, pro.ctx(image), pro.ctx(has_next ? ((item + 1) >> 1) : image), has_next, smem, q, tid, queues[tid]);
     for (int round = 0; round < D::ROUNDS_B; ++round) {
       for (int tid = 0; tid < P::NT; ++tid) phase_b_read<P>(smem, round, tid, regs[tid]);
       for (int tid = 0; tid < P::NT; ++tid) phase_b_write<P>(smem, regs[tid]);
@@ -96,6 +106,7 @@ void fft2_half_emulate(const Pro& pro, const Epi& epi, float scale, long long n_
     for (int tid = 0; tid < P::NT; ++tid)
       for (int task = tid; task < D::TASKS_C; task += P::NT) phase_c<P>(epi, ectx, smem, q, task, scale);
   }
+  delete[] queues;
   delete[] regs;
   delete[] smem;
 }

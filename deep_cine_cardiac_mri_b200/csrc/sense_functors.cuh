@@ -40,7 +40,22 @@ template <int NC> inline void red_add(cfloat* p, const float* re, const float* i
 inline void l2_prefetch_bulk(const void*, unsigned) {}
 #endif
 
-template <int NC> B2S_HD cvec<NC> ldv(const cfloat* p) { return *reinterpret_cast<const cvec<NC>*>(p); }
+// Streaming global loads bypass L1 (ld.global.cg): with ~200 KB of the SM's 256 KB used as shared
+// memory the L1 is only a few hundred lines, and an allocating load can only be in flight while it
+// owns an L1 line - that capped memory-level parallelism at ~16 KB per SM (measured, profiles/).
+#if defined(__CUDA_ARCH__)
+template <int NC> __device__ __forceinline__ cvec<NC> ldv(const cfloat* p);
+template <> __device__ __forceinline__ cvec<1> ldv<1>(const cfloat* p) {
+  const float2 t = __ldcg(reinterpret_cast<const float2*>(p));
+  cvec<1> r; r.v[0].x = t.x; r.v[0].y = t.y; return r;
+}
+template <> __device__ __forceinline__ cvec<2> ldv<2>(const cfloat* p) {
+  const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+  cvec<2> r; r.v[0].x = t.x; r.v[0].y = t.y; r.v[1].x = t.z; r.v[1].y = t.w; return r;
+}
+#else
+template <int NC> inline cvec<NC> ldv(const cfloat* p) { return *reinterpret_cast<const cvec<NC>*>(p); }
+#endif
 template <int NC> B2S_HD void stv(cfloat* p, const cvec<NC>& v) { *reinterpret_cast<cvec<NC>*>(p) = v; }
 
 // `bytes` contiguous bytes in chunks of 32 KB, one chunk per thread
@@ -56,12 +71,24 @@ template <int H, int W, bool INV> struct ProPlain {
   struct Ctx { const cfloat* p; };
   typedef const cfloat* Ptr;
   B2S_HD Ctx ctx(long long image) const { Ctx c; c.p = in + image * image_stride; return c; }
-  B2S_HD float row_weight(const Ctx&, int, int) const { return 1.f; }
-  B2S_HD Ptr task_ptr(const Ctx& c, int off) const { return c.p + off; }
-  template <int NC> B2S_HD void load(Ptr p, int off, float, float* re, float* im) const {
-    const cvec<NC> v = ldv<NC>(p + off);
+  static constexpr int QDEPTH = 5;                            // 40 loads (one task) in flight per thread
+  template <int NC> struct Unit { cvec<NC> a[8]; };
+  // raw loads of the 8 rows g + G*j of one column group (row stride RS = G*W elements)
+  template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int, int off, Unit<NC>& u) const {
+#ifndef B2S_NOLOAD
+    const cfloat* p = c.p + off;
 #pragma unroll
-    for (int n = 0; n < NC; ++n) { re[n] = INV ? v.v[n].y : v.v[n].x; im[n] = INV ? v.v[n].x : v.v[n].y; }
+    for (int j = 0; j < 8; ++j) u.a[j] = ldv<NC>(p + j * RS);
+#else   /* dev-only: compute floor of Phase A without memory traffic */
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int n = 0; n < NC; ++n) u.a[j].v[n] = make_c((float)(off + j), (float)(off - n));
+#endif
+  }
+  template <int NC> B2S_HD void value(const Unit<NC>& u, int j, float* re, float* im) const {
+#pragma unroll
+    for (int n = 0; n < NC; ++n) { re[n] = INV ? u.a[j].v[n].y : u.a[j].v[n].x; im[n] = INV ? u.a[j].v[n].x : u.a[j].v[n].y; }
   }
   B2S_HD void l2_prefetch(long long image, int tid) const { prefetch_span(in + image * image_stride, (long long)H * W * 8, tid); }
 };
@@ -74,14 +101,19 @@ template <int H, int W> struct ProExpand {
     const long long c = image % C, bt = image / C, b = bt / T;
     Ctx k; k.a = img + bt * hw; k.s = sens + (b * C + c) * hw; return k;
   }
-  B2S_HD float row_weight(const Ctx&, int, int) const { return 1.f; }
-  B2S_HD Ptr task_ptr(const Ctx& c, int off) const { Ptr p; p.a = c.a + off; p.s = c.s + off; return p; }
-  template <int NC> B2S_HD void load(const Ptr& p, int off, float, float* re, float* im) const {
-    const cvec<NC> a = ldv<NC>(p.a + off), s = ldv<NC>(p.s + off);
+  static constexpr int QDEPTH = 2;                            // 2 x 16 loads in flight per thread
+  template <int NC> struct Unit { cvec<NC> a[8], s[8]; };
+  template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int, int off, Unit<NC>& u) const {
+    const cfloat* pa = c.a + off; const cfloat* ps = c.s + off;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { u.a[j] = ldv<NC>(pa + j * RS); u.s[j] = ldv<NC>(ps + j * RS); }
+  }
+  template <int NC> B2S_HD void value(const Unit<NC>& u, int j, float* re, float* im) const {
 #pragma unroll
     for (int n = 0; n < NC; ++n) {
-      re[n] = a.v[n].x * s.v[n].x - a.v[n].y * s.v[n].y;
-      im[n] = a.v[n].x * s.v[n].y + a.v[n].y * s.v[n].x;
+      const cfloat a = u.a[j].v[n], s = u.s[j].v[n];
+      re[n] = a.x * s.x - a.y * s.y;
+      im[n] = a.x * s.y + a.y * s.x;
     }
   }
   B2S_HD void l2_prefetch(long long, int) const {}             // image and maps are L2 resident
@@ -99,15 +131,22 @@ template <int H, int W, int WMODE> struct ProKspace {
     if (WMODE == 2) { const float v = *vptr; c.wb = -v / (1.f + v); }
     return c;
   }
-  B2S_HD float row_weight(const Ctx& c, int g, int off) const {
-    return WMODE ? c.wa + c.wb * (float)c.m[g + off] : 1.f;
-  }
-  B2S_HD Ptr task_ptr(const Ctx& c, int off) const { return c.p + off; }
-  template <int NC> B2S_HD void load(Ptr p, int off, float w, float* re, float* im) const {
-    const cvec<NC> v = ldv<NC>(p + off);                  // inverse transform: feed swapped
+  static constexpr int QDEPTH = 5;
+  template <int NC> struct Unit { cvec<NC> a[8]; float w[WMODE ? 8 : 1]; };
+  template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int g, int off, Unit<NC>& u) const {
+    const cfloat* p = c.p + off;
 #pragma unroll
-    for (int n = 0; n < NC; ++n) {
-      if (WMODE) { re[n] = v.v[n].y * w; im[n] = v.v[n].x * w; } else { re[n] = v.v[n].y; im[n] = v.v[n].x; }
+    for (int j = 0; j < 8; ++j) u.a[j] = ldv<NC>(p + j * RS);
+    if (WMODE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u.w[j] = c.wa + c.wb * (float)c.m[g + j * (RS / W)];
+    }
+  }
+  template <int NC> B2S_HD void value(const Unit<NC>& u, int j, float* re, float* im) const {
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {                       // inverse transform: feed swapped
+      if (WMODE) { re[n] = u.a[j].v[n].y * u.w[j]; im[n] = u.a[j].v[n].x * u.w[j]; }
+      else { re[n] = u.a[j].v[n].y; im[n] = u.a[j].v[n].x; }
     }
   }
   B2S_HD void l2_prefetch(long long image, int tid) const { prefetch_span(k + image * hw, (long long)H * W * 8, tid); }
@@ -120,10 +159,15 @@ template <int H, int W, bool INV> struct EpiPlain {
   typedef cfloat* Ptr;
   B2S_HD Ctx ctx(long long image) const { Ctx c; c.p = out + image * image_stride; return c; }
   B2S_HD Ptr task_ptr(const Ctx& c, int m, int kx) const { return c.p + m * W + kx; }
-  template <int NC> B2S_HD void store(Ptr p, int k, const float* re, const float* im) const {
+  template <int G, int NC> struct Pre {};
+  template <int G, int NC> B2S_HD void prefetch(Ptr, Pre<G, NC>&) const {}
+  template <int G, int NC> B2S_HD void store(Ptr p, int k, const float* re, const float* im, const Pre<G, NC>&) const {
     cvec<NC> v;
 #pragma unroll
     for (int n = 0; n < NC; ++n) v.v[n] = INV ? make_c(im[n], re[n]) : make_c(re[n], im[n]);
+#ifdef B2S_NOSTORE  /* dev-only: compute floor of Phase C */
+    if (v.v[0].x == 123.456f)
+#endif
     stv<NC>(p + 8 * k * W, v);
   }
   B2S_HD void l2_prefetch(long long, int, int) const {}
@@ -146,15 +190,29 @@ template <int H, int W, int MODE> struct EpiKspace {
     t.p = c.p + off; t.r = (MODE >= 2) ? c.r + off : nullptr; t.m = (MODE >= 1) ? c.m + m : nullptr; t.v = c.v;
     return t;
   }
-  template <int NC> B2S_HD void store(const Ptr& t, int k, const float* re_in, const float* im_in) const {
-    const bool mk = (MODE >= 1) ? (t.m[8 * k] != 0) : true;
+  template <int G, int NC> struct Pre { cvec<NC> r[(MODE >= 2) ? G : 1]; unsigned mbits; };
+  template <int G, int NC> B2S_HD void prefetch(const Ptr& t, Pre<G, NC>& pre) const {
+    pre.mbits = 0xffffffffu;
+    if (MODE >= 1) {
+      pre.mbits = 0u;
+#pragma unroll
+      for (int k = 0; k < G; ++k) pre.mbits |= (t.m[8 * k] ? 1u : 0u) << k;
+    }
+    if (MODE >= 2) {
+#pragma unroll
+      for (int k = 0; k < G; ++k)                          // DC needs ref on sampled rows only
+        if (MODE == 3 || ((pre.mbits >> k) & 1u)) pre.r[k] = ldv<NC>(t.r + 8 * k * W);
+    }
+  }
+  template <int G, int NC> B2S_HD void store(const Ptr& t, int k, const float* re_in, const float* im_in, const Pre<G, NC>& pre) const {
+    const bool mk = (pre.mbits >> k) & 1u;
     cvec<NC> o;
     if (MODE <= 1) {
 #pragma unroll
       for (int n = 0; n < NC; ++n) o.v[n] = mk ? make_c(re_in[n], im_in[n]) : make_c(0.f, 0.f);
     } else if (MODE == 2) {
-      if (mk) {                                             // ref is only needed on sampled rows
-        const cvec<NC> r = ldv<NC>(t.r + 8 * k * W);
+      if (mk) {
+        const cvec<NC> r = pre.r[k];
 #pragma unroll
         for (int n = 0; n < NC; ++n)
           o.v[n] = make_c((re_in[n] + t.v * r.v[n].x) / (1.f + t.v), (im_in[n] + t.v * r.v[n].y) / (1.f + t.v));
@@ -163,7 +221,7 @@ template <int H, int W, int MODE> struct EpiKspace {
         for (int n = 0; n < NC; ++n) o.v[n] = make_c(re_in[n], im_in[n]);
       }
     } else {
-      const cvec<NC> r = ldv<NC>(t.r + 8 * k * W);
+      const cvec<NC> r = pre.r[k];
 #pragma unroll
       for (int n = 0; n < NC; ++n)
         o.v[n] = mk ? make_c(re_in[n] - r.v[n].x, im_in[n] - r.v[n].y) : make_c(0.f - r.v[n].x, 0.f - r.v[n].y);
@@ -188,8 +246,13 @@ template <int H, int W> struct EpiReduce {
     return k;
   }
   B2S_HD Ptr task_ptr(const Ctx& c, int m, int kx) const { Ptr t; t.o = c.o + m * W + kx; t.m = c.m + m * W + kx; return t; }
-  template <int NC> B2S_HD void store(const Ptr& t, int k, const float* re, const float* im) const {
-    const cvec<NC> s = ldv<NC>(t.m + 8 * k * W);
+  template <int G, int NC> struct Pre { cvec<NC> s[G]; };
+  template <int G, int NC> B2S_HD void prefetch(const Ptr& t, Pre<G, NC>& pre) const {
+#pragma unroll
+    for (int k = 0; k < G; ++k) pre.s[k] = ldv<NC>(t.m + 8 * k * W);
+  }
+  template <int G, int NC> B2S_HD void store(const Ptr& t, int k, const float* re, const float* im, const Pre<G, NC>& pre) const {
+    const cvec<NC> s = pre.s[k];
     float ar[NC], ai[NC];
 #pragma unroll
     for (int n = 0; n < NC; ++n) {

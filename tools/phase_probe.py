@@ -4,7 +4,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
 from deep_cine_cardiac_mri_b200 import ops, _lib
 lib = _lib.lib()
-b, t, c, h, w = 4, 15, 10, 200, 200
+b, t, c, h, w = [int(v) for v in (sys.argv[1:6] if len(sys.argv) > 5 else (4, 15, 10, 200, 200))]
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 k = torch.randn(b, t, c, h, w, 2, device=dev, generator=g)
