@@ -33,9 +33,14 @@ template <int H_, int XC_> struct NormalPlan {
   static_assert(H_ % 8 == 0, "H must be a multiple of 8");
 };
 
+// mode 0: out = A^H M A x + v x                        (HOperator, cinenet.py:121-133)
+// mode 1: out = ssq . x - eta (A^H M A x - bref)        (one VarNet cascade in the image domain:
+//         A^H[ DC(A x, ref) ] with ssq = sum_c |S_c|^2, bref = A^H ref, eta = v/(1+v); varnet.py:253-282
+//         followed by the next cascade's / the model's sens_reduce, varnet.py:150-151,253)
 struct NormalArgs {
   const cfloat* x; const cfloat* sens; const uint8_t* mask; const float* vptr; cfloat* out;
   int T, C, W;
+  int mode; const float* ssq; const cfloat* bref;
 };
 
 // step 1: p = S_c x, radix-G over this thread's rows, twiddle, store E[g][m][xl]
@@ -118,11 +123,19 @@ B2S_HD void normal_finish(const NormalArgs& a, long long bt, int x0, int tid, co
   constexpr int G = P::G, XC = P::XC;
   const int m = tid / XC, xl = tid - m * XC, x = x0 + xl;
   const long long hw = (long long)P::H * a.W;
+  const float eta = v / (1.f + v);
 #pragma unroll
   for (int k = 0; k < G; ++k) {
-    const long long off = bt * hw + (long long)(m + 8 * k) * a.W + x;
+    const long long pix = (long long)(m + 8 * k) * a.W + x;
+    const long long off = bt * hw + pix;
     const cfloat xv = a.x[off];
-    a.out[off] = make_c(accr[k] + v * xv.x, acci[k] + v * xv.y);
+    if (a.mode == 0) {
+      a.out[off] = make_c(accr[k] + v * xv.x, acci[k] + v * xv.y);
+    } else {
+      const float d = a.ssq[(bt / a.T) * hw + pix];
+      const cfloat br = a.bref[off];
+      a.out[off] = make_c(d * xv.x - eta * (accr[k] - br.x), d * xv.y - eta * (acci[k] - br.y));
+    }
   }
 }
 

@@ -162,6 +162,16 @@ def raw_normal_op(x, sens, mask_u8, v):
     return out
 
 
+def raw_normal_dc(x, sens, mask_u8, v, ssq, bref):
+    """One image-domain VarNet DC cascade: ssq*x - v/(1+v) (A^H M A x - bref)  (inference path, h == 200)."""
+    _need_cuda(x, sens, mask_u8, v, ssq, bref)
+    b, t, h, w, _ = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().b2s_normal_dc(_p(x), _p(sens), _p(mask_u8), _p(v), _p(ssq), _p(bref), _p(out), b, t,
+                                        sens.shape[1], h, w, _stream()), "normal_dc")
+    return out
+
+
 def normal_op_supported(h: int, w: int) -> bool:
     return h == 200 and w % 20 == 0
 

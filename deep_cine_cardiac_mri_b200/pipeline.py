@@ -48,6 +48,38 @@ def varnet_hot_path(masked_kspace: torch.Tensor, mask: torch.Tensor,
     return F.complex_abs(ops.sens_reduce(k, sens))
 
 
+def varnet_hot_path_image_domain(masked_kspace: torch.Tensor, mask: torch.Tensor,
+                                 v: Union[float, torch.Tensor, Sequence] = 1.0, n_cascades: int = 12, xf: bool = True,
+                                 regulariser: Optional[Callable] = None, sens_unet: Optional[Callable] = None,
+                                 sens_maps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Same function as `varnet_hot_path` (inference), without ever materialising k-space.
+
+    Between cascades the predicted k-space is only consumed by the next `sens_reduce`
+    (varnet.py:253) or by the final one (varnet.py:150-151), and
+        A^H[ DC(A x, ref) ] = (sum_c |S_c|^2) x - eta (A^H M A x - A^H ref),   eta = v/(1+v),
+    because F^H F = I and the mask commutes with the transform along w.  Each cascade is one
+    launch of the on-chip normal-operator kernel (b2s_normal_dc): 2I + S bytes instead of 3K + 2I + 2S.
+    """
+    b, t, c, h, w, _ = masked_kspace.shape
+    if not ops.normal_op_supported(h, w) or (torch.is_grad_enabled() and masked_kspace.requires_grad):
+        return varnet_hot_path(masked_kspace, mask, v, n_cascades, xf, regulariser, sens_unet, sens_maps)
+    sens = sensitivity_maps(masked_kspace, mask, sens_unet) if sens_maps is None else sens_maps
+    s5 = ops._f32c(sens.squeeze(1))
+    m8 = ops._mask_u8(mask, b, t, h)
+    vs = list(v) if isinstance(v, (list, tuple)) else [v] * n_cascades
+    vs = [x.detach().reshape(1) if isinstance(x, torch.Tensor) else ops._vdev(x, masked_kspace.device) for x in vs]
+    ssq = F.complex_abs_sq(s5).sum(dim=1).contiguous()                     # (b,h,w)  sum_c |S_c|^2
+    bref = ops.raw_sens_reduce(ops._f32c(masked_kspace), s5, ops.REDUCE_MASK, False, m8, None, 1)   # A^H M ref
+    img = bref                                                             # cascade 0 starts from k = ref
+    for i in range(n_cascades):
+        x, mean = ops.raw_temporal_pre(img, xf)
+        if regulariser is not None:
+            x = regulariser(x.unsqueeze(2)).squeeze(2).contiguous()
+        model_out = ops.raw_temporal_post(x, mean, xf)
+        img = ops.raw_normal_dc(model_out, s5, m8, vs[i], ssq, bref)
+    return F.complex_abs(img)
+
+
 def hot_path_algorithmic_bytes(b: int, t: int, c: int, h: int, w: int, n_cascades: int) -> dict:
     """Algorithmic HBM bytes of the calls above, fp32."""
     K, I, S = b * t * c * h * w * 8, b * t * h * w * 8, b * c * h * w * 8

@@ -128,6 +128,12 @@ int b2s_temporal_post(const float* x, const float* mean, float* out, int b, int 
  * F_w cancels and H x = sum_c conj(S_c) * (F_h^H M F_h)(S_c x) + v x.  x, out (b,t,h,w,2). */
 int b2s_normal_op(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out,
                   int b, int t, int c, int h, int w, void* stream);
+/* One VarNet cascade's data-consistency step entirely in the image domain (k-space never exists):
+ *   out = A^H[ DC(A x, ref) ] = ssq . x - v/(1+v) (A^H M A x - bref),   ssq = sum_c |S_c|^2 (b,h,w),
+ *   bref = A^H ref (b,t,h,w,2).  Replaces varnet.py:257 + 281-282 of cascade n together with the
+ *   sens_reduce of cascade n+1 (varnet.py:253) / of VarNet.forward (varnet.py:150-151). */
+int b2s_normal_dc(const float* x, const float* sens, const uint8_t* mask, const float* v, const float* ssq,
+                  const float* bref, float* out, int b, int t, int c, int h, int w, void* stream);
 /* CG scalar/vector kernels with alpha, beta kept in device memory (no .item() syncs):
  * dot: out[0] = <a,b> over n floats (deterministic two-stage; scratch >= 1024 floats) */
 int b2s_dot(const float* a, const float* b, float* out, int64_t n, float* scratch, void* stream);

@@ -82,7 +82,16 @@ extern "C" int emu_normal_op(const float* x, const float* sens, const uint8_t* m
   typedef NormalPlan<200, 20> P;
   if (h != 200 || w % 20) return 2;
   NormalArgs a; a.x = (const cfloat*)x; a.sens = (const cfloat*)sens; a.mask = mask; a.vptr = v; a.out = (cfloat*)out;
-  a.T = t; a.C = c; a.W = w;
+  a.T = t; a.C = c; a.W = w; a.mode = 0; a.ssq = nullptr; a.bref = nullptr;
+  normal_op_emulate<P>(a, (long long)b * t);
+  return 0;
+}
+extern "C" int emu_normal_dc(const float* x, const float* sens, const uint8_t* mask, const float* v, const float* ssq,
+                             const float* bref, float* out, int b, int t, int c, int h, int w) {
+  typedef NormalPlan<200, 20> P;
+  if (h != 200 || w % 20) return 2;
+  NormalArgs a; a.x = (const cfloat*)x; a.sens = (const cfloat*)sens; a.mask = mask; a.vptr = v; a.out = (cfloat*)out;
+  a.T = t; a.C = c; a.W = w; a.mode = 1; a.ssq = ssq; a.bref = (const cfloat*)bref;
   normal_op_emulate<P>(a, (long long)b * t);
   return 0;
 }

@@ -139,6 +139,21 @@ def test_emulated_normal_operator(emu):
     assert rel(out, O.normal_op(d["img"], d["mask"], d["sens"], float(v[0]))) <= 1e-6
 
 
+def test_emulated_image_domain_cascade(emu):
+    """b2s_normal_dc == A^H[DC(A x, ref)] (one VarNet cascade without materialising k-space)."""
+    b, t, c, h, w = 1, 2, 3, 200, 200
+    cs = G.sense_case(9, b, t, c, h, w)
+    d = {k: (a.astype(np.float64) if getattr(a, "dtype", None) == np.float32 and a.ndim else a) for k, a in cs.items()}
+    v = np.array([0.8], dtype=np.float32)
+    ref_m = O.apply_mask(d["ref"], d["mask"])
+    bref = np.ascontiguousarray(O.sens_reduce(ref_m, d["sens"]).astype(np.float32))
+    ssq = np.ascontiguousarray((d["sens"] ** 2).sum(axis=(2, 5))[:, 0].astype(np.float32))
+    want = O.sens_reduce(O.dc_blend(O.sens_expand(d["img"], d["sens"]), ref_m, d["mask"], 0.8), d["sens"])
+    out = np.empty((b, t, 1, h, w, 2), np.float32)
+    assert emu.emu_normal_dc(P(cs["img"]), P(cs["sens"]), P(cs["mask"]), P(v), P(ssq), P(bref), P(out), b, t, c, h, w) == 0
+    assert rel(out, want) <= 1e-6
+
+
 # ------------------------------------------------------------------ host logic
 def test_functional_error_parity_on_cpu_tensors():
     from deep_cine_cardiac_mri_b200 import functional as F

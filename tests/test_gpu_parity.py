@@ -188,6 +188,38 @@ def test_sens_model_and_temporal(ops):
     assert rel(blocks.xpd_temporal_ifft(cu(ibuf[:, :, 0]), 5), O.xpd_temporal_ifft(f64(ibuf[:, :, 0]), 5)) <= TOL
 
 
+def test_whole_hot_path_and_image_domain_variant(ops):
+    """pipeline.varnet_hot_path (block-faithful) == image-domain variant == oracle chain, 3 cascades."""
+    from deep_cine_cardiac_mri_b200 import pipeline, synth
+    b, t, c, h, w = 2, 5, 4, 200, 200
+    case = synth.cine_case(11, b, t, c, h, w)
+    mk, mask = cu(case["masked_kspace"]), cu(case["mask"])
+    vs = [0.5, 1.0, 2.0]
+    with torch.no_grad():
+        a = pipeline.varnet_hot_path(mk, mask, vs, 3)
+        bb = pipeline.varnet_hot_path_image_domain(mk, mask, vs, 3)
+    want = []
+    for i in range(b):                                             # the reference's SensitivityModel assumes b == 1
+        mk64, m1 = f64(case["masked_kspace"][i:i + 1]), case["mask"][i:i + 1]
+        sens = O.divide_root_sum_of_squares(O.sens_model_pre(mk64, m1))[:, None]
+        k = mk64
+        for v in vs:
+            img = O.sens_reduce(k, sens)
+            x, mean = O.temporal_pre(img[:, :, 0])
+            k = O.dc_blend(O.sens_expand(O.temporal_post(x[:, :, None], mean), sens), mk64, m1, v)
+        want.append(O.complex_abs(O.sens_reduce(k, sens, keepdim=False)))
+    want = np.concatenate(want, 0)
+    assert rel(a, want) <= 2e-5
+    assert rel(bb, want) <= 2e-5
+    # reconstruction-quality parity (SSIM / NMSE / PSNR of the two paths against the oracle output)
+    for got in (a, bb):
+        g = got.cpu().numpy().astype(np.float64)
+        for i in range(b):
+            assert O.nmse(want[i], g[i]) <= 1e-9
+            assert O.psnr(want[i], g[i]) >= 90
+            assert O.ssim(want[i], g[i]) >= 1 - 1e-6
+
+
 # ------------------------------- golden fixtures ---------------------------- #
 GOLD = np.load(G.HERE / "golden_v1.npz")
 
