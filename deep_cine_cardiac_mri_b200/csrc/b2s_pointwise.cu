@@ -4,6 +4,7 @@
 // kernels.  All are grid-stride, 64/128-bit vectorised, one pass over HBM.
 #include "b2s_common.cuh"
 #include "fft2_core.cuh"
+#include "codelets.cuh"
 
 using namespace b2s;
 
@@ -303,6 +304,63 @@ __global__ void temporal_kernel(const cfloat* in, const cfloat* mean_in, cfloat*
   }
 }
 
+// Register-codelet version for the common frame counts: each thread holds its pixel's T samples,
+// the centring rolls are compile-time index maps, the inverse uses the re/im swap.
+template <int T>
+__global__ void __launch_bounds__(128) temporal_codelet_kernel(const cfloat* __restrict__ in, const cfloat* __restrict__ mean_in,
+                                                               cfloat* __restrict__ out, cfloat* __restrict__ mean_out,
+                                                               long long hw, long long n_pix, int xf, int post) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pix) return;
+  const long long b = i / hw, p = i % hw;
+  const cfloat* src = in + b * T * hw + p;
+  cfloat* dst = out + b * T * hw + p;
+  constexpr int S_IN = (T + 1) / 2, S_OUT = T / 2;
+  float re[T], im[T];
+  cfloat mu = make_c(0.f, 0.f);
+  cfloat v[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) v[t] = src[(long long)t * hw];
+  if (!post) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) { mu.x += v[t].x; mu.y += v[t].y; }
+    mu.x *= (1.f / (float)T); mu.y *= (1.f / (float)T);
+    mean_out[i] = mu;
+#pragma unroll
+    for (int t = 0; t < T; ++t) { v[t].x -= mu.x; v[t].y -= mu.y; }
+  } else {
+    mu = mean_in[i];
+  }
+  if (!xf) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) dst[(long long)t * hw] = post ? make_c(v[t].x + mu.x, v[t].y + mu.y) : v[t];
+    return;
+  }
+  // z[e] = x[(e - S_IN) mod T]
+#pragma unroll
+  for (int e = 0; e < T; ++e) {
+    const int t = (e - S_IN + T) % T;
+    re[e] = post ? v[t].y : v[t].x;               // inverse: swapped
+    im[e] = post ? v[t].x : v[t].y;
+  }
+  Dft<T>::run(re, im);
+  const float sc = rsqrtf((float)T);
+#pragma unroll
+  for (int kk = 0; kk < T; ++kk) {                 // Y[kk] = X[(kk - S_OUT) mod T]
+    const int k = (kk - S_OUT + T) % T;
+    const float a = (post ? im[k] : re[k]) * sc, c = (post ? re[k] : im[k]) * sc;
+    dst[(long long)kk * hw] = post ? make_c(a + mu.x, c + mu.y) : make_c(a, c);
+  }
+}
+
+template <int T>
+static int launch_temporal_codelet(const float* in, const float* mean_in, float* out, float* mean_out, long long hw,
+                                   long long n_pix, int xf, int post, cudaStream_t st) {
+  temporal_codelet_kernel<T><<<(unsigned)((n_pix + 127) / 128), 128, 0, st>>>((const cfloat*)in, (const cfloat*)mean_in, (cfloat*)out,
+                                                                            (cfloat*)mean_out, hw, n_pix, xf, post);
+  return check_launch("temporal_codelet_kernel");
+}
+
 // --------------------------------- CG kernels ------------------------------ //
 __global__ void dot_partial_kernel(const float* a, const float* b, float* partial, long long n) {
   float acc = 0.f;
@@ -453,6 +511,12 @@ static int launch_temporal(const float* in, const float* mean_in, float* out, fl
   if (t < 1 || t > 192) return fail(B2S_EUNSUPPORTED, "temporal length must be in [1, 192]");
   const long long n_pix = (long long)b * hw;
   if (n_pix == 0) return B2S_OK;
+  switch (t) {                                             // register codelets for the usual frame counts
+#define B2S_T(N) case N: return launch_temporal_codelet<N>(in, mean_in, out, mean_out, hw, n_pix, xf, post, (cudaStream_t)stream);
+    B2S_T(12) B2S_T(15) B2S_T(16) B2S_T(20) B2S_T(24) B2S_T(25) B2S_T(30) B2S_T(32)
+#undef B2S_T
+    default: break;
+  }
   int block = (int)(5632 / t) / 32 * 32;                   // t * block * 8 B + tw <= 48 KB
   if (block > 128) block = 128;
   if (block < 32) block = 32;

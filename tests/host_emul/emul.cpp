@@ -95,3 +95,25 @@ extern "C" int emu_normal_dc(const float* x, const float* sens, const uint8_t* m
   normal_op_emulate<P>(a, (long long)b * t);
   return 0;
 }
+
+// every generated codelet against a direct DFT (double), returns the worst relative error
+template <int N> static double codelet_err() {
+  float re[N], im[N]; double xr[N], xi[N];
+  for (int j = 0; j < N; ++j) { xr[j] = sin(1.0 + j * 0.7) + 0.1 * j; xi[j] = cos(2.0 + j * 1.3); re[j] = (float)xr[j]; im[j] = (float)xi[j]; }
+  Dft<N>::run(re, im);
+  double err = 0, mx = 0;
+  for (int k = 0; k < N; ++k) {
+    double sr = 0, si = 0;
+    for (int j = 0; j < N; ++j) { const double a = -2.0 * M_PI * j * k / N; sr += xr[j] * cos(a) - xi[j] * sin(a); si += xr[j] * sin(a) + xi[j] * cos(a); }
+    err = fmax(err, hypot(sr - re[k], si - im[k])); mx = fmax(mx, hypot(sr, si));
+  }
+  return err / mx;
+}
+extern "C" double emu_codelet_worst_error() {
+  double e = 0;
+  e = fmax(e, codelet_err<2>()); e = fmax(e, codelet_err<3>()); e = fmax(e, codelet_err<4>()); e = fmax(e, codelet_err<5>());
+  e = fmax(e, codelet_err<8>()); e = fmax(e, codelet_err<10>()); e = fmax(e, codelet_err<12>()); e = fmax(e, codelet_err<15>());
+  e = fmax(e, codelet_err<16>()); e = fmax(e, codelet_err<20>()); e = fmax(e, codelet_err<24>()); e = fmax(e, codelet_err<25>());
+  e = fmax(e, codelet_err<30>()); e = fmax(e, codelet_err<32>()); e = fmax(e, codelet_err<40>());
+  return e;
+}

@@ -90,6 +90,11 @@ def rel(a, b):
     return float(np.abs(a - b).max() / np.abs(b).max())
 
 
+def test_generated_codelets(emu):
+    emu.emu_codelet_worst_error.restype = ctypes.c_double
+    assert emu.emu_codelet_worst_error() <= 2e-7          # dft2 ... dft40 vs a direct double DFT
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_emulated_fft2c(emu, variant):
     emu.emu_set_variant(variant)

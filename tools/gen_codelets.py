@@ -22,7 +22,7 @@ import math
 from pathlib import Path
 
 OUT = Path(__file__).resolve().parents[1] / "deep_cine_cardiac_mri_b200" / "csrc" / "codelets.cuh"
-SIZES = [2, 3, 4, 5, 8, 10, 16, 20, 25, 32, 40]
+SIZES = [2, 3, 4, 5, 8, 10, 12, 15, 16, 20, 24, 25, 30, 32, 40]
 EPS = 1e-12
 
 
