@@ -73,7 +73,8 @@ template <class P> struct Derived {
   static constexpr int TW_OFF = B_ELEMS;                        // TW[W]
   static constexpr int TH_OFF = TW_OFF + P::W;                  // TH[2][G][4] (both halves q)
   static constexpr int SMEM_ELEMS = TH_OFF + 2 * P::G * 4;
-  static constexpr int SMEM_BYTES = SMEM_ELEMS * 8;
+  static constexpr int MASK_BYTES = (P::H + 15) / 16 * 16;      // this item's mask row (uint8) after the tables
+  static constexpr int SMEM_BYTES = SMEM_ELEMS * 8 + MASK_BYTES;
   static constexpr int XP = P::X0 / P::NC;                      // column groups per row group
   static constexpr int TASKS_A = P::G * XP;
   static constexpr int KXP = P::W / P::NC;

@@ -24,6 +24,7 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
   using D = Derived<P>;
   extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
   cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);
+  uint8_t* mrow = reinterpret_cast<uint8_t*>(smem + D::SMEM_ELEMS);
   const int tid = threadIdx.x;
 
   build_tables<P>(smem, tid, P::NT);
@@ -50,13 +51,15 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
     const int q = item & 1;
     const int next = item + (int)gridDim.x;
     const bool has_next = next < n_items;
-    epi.l2_prefetch(image, q, tid);                        // what Phase C will read
+    epi.stage_mask(image, mrow, tid, P::NT);               // visible to Phase C through the barriers below
     if (!CARRY) PA::prefill(pro, pro.ctx(image), tid, queue);
     PA::run(pro, pro.ctx(image), pro.ctx(has_next ? (next >> 1) : image), CARRY && has_next, smem, q, tid, queue);
     __syncthreads();
     B2S_TICK(0);
     // warm L2 with the rest of the next item while this SM is busy with register codelets (Phases B, C)
     if (has_next && !(next & 1)) pro.l2_prefetch(next >> 1, tid);
+    epi.l2_prefetch(image, q, tid);                        // what Phase C will read (issued here, not before
+                                                           // Phase A: bulk prefetches compete with its demand loads)
 
 #pragma unroll 1
     for (int round = 0; round < D::ROUNDS_B; ++round) {
@@ -70,7 +73,7 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
     }
 
     {
-      const typename Epi::Ctx ectx = epi.ctx(image);
+      const typename Epi::Ctx ectx = epi.ctx(image, mrow);
       for (int task = tid; task < D::TASKS_C; task += P::NT) phase_c<P>(epi, ectx, smem, q, task, scale);
     }
     __syncthreads();                                       // B is rewritten by the next item's Phase A
@@ -86,6 +89,7 @@ void fft2_half_emulate(const Pro& pro, const Epi& epi, float scale, long long n_
   using D = Derived<P>;
   typedef PhaseA<P, Pro> PA;
   cfloat* smem = new cfloat[D::SMEM_ELEMS];
+  uint8_t* mrow = new uint8_t[D::MASK_BYTES];
   PhaseBRegs<P>* regs = new PhaseBRegs<P>[P::NT];
   typename PA::Queue* queues = new typename PA::Queue[P::NT];
   for (int i = 0; i < D::SMEM_ELEMS; ++i) smem[i] = make_c(0.f, 0.f);
@@ -96,7 +100,8 @@ void fft2_half_emulate(const Pro& pro, const Epi& epi, float scale, long long n_
     const long long image = item >> 1;
     const int q = (int)(item & 1);
     const bool has_next = item + 1 < n_items;
-    const typename Epi::Ctx ectx = epi.ctx(image);
+    for (int tid = 0; tid < P::NT; ++tid) epi.stage_mask(image, mrow, tid, P::NT);
+    const typename Epi::Ctx ectx = epi.ctx(image, mrow);
     for (int tid = 0; tid < P::NT; ++tid)
       PA::run(pro, pro.ctx(image), pro.ctx(has_next ? ((item + 1) >> 1) : image), has_next, smem, q, tid, queues[tid]);
     for (int round = 0; round < D::ROUNDS_B; ++round) {
@@ -108,6 +113,7 @@ void fft2_half_emulate(const Pro& pro, const Epi& epi, float scale, long long n_
   }
   delete[] queues;
   delete[] regs;
+  delete[] mrow;
   delete[] smem;
 }
 

@@ -26,7 +26,8 @@ template <int H_, int XC_> struct NormalPlan {
   static constexpr int H = H_, G = H_ / 8, XC = XC_;
   static constexpr int NT = 8 * XC_;
   static constexpr int E_ELEMS = H_ * XC_;           // exchange buffer [g][m][x]
-  static constexpr int TW_OFF = E_ELEMS;             // w_H^n, n in [0,H)
+  static constexpr int X_OFF = E_ELEMS;              // this CTA's columns of x_t, [row][x] (read by every coil)
+  static constexpr int TW_OFF = X_OFF + H_ * XC_;    // w_H^n, n in [0,H)
   static constexpr int SMEM_ELEMS = TW_OFF + H_;
   static constexpr int SMEM_BYTES = SMEM_ELEMS * 8 + H_;   // + mask row (uint8)
   static constexpr int TASKS2 = G * XC_;
@@ -43,23 +44,33 @@ struct NormalArgs {
   int mode; const float* ssq; const cfloat* bref;
 };
 
-// step 1: p = S_c x, radix-G over this thread's rows, twiddle, store E[g][m][xl]
+// step 0 (once per CTA): this thread's rows {m + 8i} of x_t into shared memory
 template <class P>
-B2S_HD void normal_step1(const NormalArgs& a, cfloat* smem, long long bt, int c, int x0, int tid) {
+B2S_HD void normal_stage_x(const NormalArgs& a, cfloat* smem, long long bt, int x0, int tid) {
+  constexpr int G = P::G, XC = P::XC;
+  const int m = tid / XC, xl = tid - m * XC;
+  const cfloat* xp = a.x + bt * (long long)P::H * a.W + x0 + xl;
+#pragma unroll
+  for (int i = 0; i < G; ++i) smem[P::X_OFF + (m + 8 * i) * XC + xl] = xp[(long long)(m + 8 * i) * a.W];
+}
+
+// step 1: p = S_c x, radix-G over this thread's rows, twiddle, store E[g][m][xl]; S_c values stay in sv
+template <class P>
+B2S_HD void normal_step1(const NormalArgs& a, cfloat* smem, long long bt, int c, int x0, int tid, cfloat (&sv)[P::G]) {
   constexpr int G = P::G, XC = P::XC;
   const int m = tid / XC, xl = tid - m * XC, x = x0 + xl;
   const long long b = bt / a.T;
   const long long hw = (long long)P::H * a.W;
-  const cfloat* xp = a.x + bt * hw + x;
   const cfloat* sp = a.sens + (b * a.C + c) * hw + x;
   float re[G], im[G];
   const float sg = (m & 1) ? -1.f : 1.f;
 #pragma unroll
+  for (int i = 0; i < G; ++i) sv[i] = sp[(long long)(m + 8 * i) * a.W];
+#pragma unroll
   for (int i = 0; i < G; ++i) {
-    const long long row = (long long)(m + 8 * i) * a.W;
-    const cfloat xv = xp[row], sv = sp[row];
-    re[i] = (xv.x * sv.x - xv.y * sv.y) * sg;
-    im[i] = (xv.x * sv.y + xv.y * sv.x) * sg;
+    const cfloat xv = smem[P::X_OFF + (m + 8 * i) * XC + xl];
+    re[i] = (xv.x * sv[i].x - xv.y * sv[i].y) * sg;
+    im[i] = (xv.x * sv[i].y + xv.y * sv[i].x) * sg;
   }
   Dft<G>::run(re, im);
   const cfloat* tw = smem + P::TW_OFF;
@@ -96,13 +107,10 @@ B2S_HD void normal_step2(cfloat* smem, const uint8_t* mrow, int task) {
 
 // step 3: radix-G over g -> rows m + 8k (swapped domain), un-swap, sign, conj(S_c), accumulate
 template <class P>
-B2S_HD void normal_step3(const NormalArgs& a, const cfloat* smem, long long bt, int c, int x0, int tid,
+B2S_HD void normal_step3(const cfloat* smem, int tid, const cfloat (&sv)[P::G],
                          float (&accr)[P::G], float (&acci)[P::G], float scale) {
   constexpr int G = P::G, XC = P::XC;
-  const int m = tid / XC, xl = tid - m * XC, x = x0 + xl;
-  const long long b = bt / a.T;
-  const long long hw = (long long)P::H * a.W;
-  const cfloat* sp = a.sens + (b * a.C + c) * hw + x;
+  const int m = tid / XC, xl = tid - m * XC;
   float re[G], im[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) { const cfloat v = smem[(g * 8 + m) * XC + xl]; re[g] = v.x; im[g] = v.y; }
@@ -110,15 +118,14 @@ B2S_HD void normal_step3(const NormalArgs& a, const cfloat* smem, long long bt, 
   const float s = (m & 1) ? -scale : scale;
 #pragma unroll
   for (int k = 0; k < G; ++k) {
-    const cfloat sv = sp[(long long)(m + 8 * k) * a.W];
     const float yr = im[k] * s, yi = re[k] * s;        // un-swap
-    accr[k] += yr * sv.x + yi * sv.y;
-    acci[k] += yi * sv.x - yr * sv.y;
+    accr[k] += yr * sv[k].x + yi * sv[k].y;
+    acci[k] += yi * sv[k].x - yr * sv[k].y;
   }
 }
 
 template <class P>
-B2S_HD void normal_finish(const NormalArgs& a, long long bt, int x0, int tid, const float (&accr)[P::G],
+B2S_HD void normal_finish(const NormalArgs& a, const cfloat* smem, long long bt, int x0, int tid, const float (&accr)[P::G],
                           const float (&acci)[P::G], float v) {
   constexpr int G = P::G, XC = P::XC;
   const int m = tid / XC, xl = tid - m * XC, x = x0 + xl;
@@ -128,7 +135,7 @@ B2S_HD void normal_finish(const NormalArgs& a, long long bt, int x0, int tid, co
   for (int k = 0; k < G; ++k) {
     const long long pix = (long long)(m + 8 * k) * a.W + x;
     const long long off = bt * hw + pix;
-    const cfloat xv = a.x[off];
+    const cfloat xv = smem[P::X_OFF + (m + 8 * k) * XC + xl];
     if (a.mode == 0) {
       a.out[off] = make_c(accr[k] + v * xv.x, acci[k] + v * xv.y);
     } else {
@@ -141,7 +148,7 @@ B2S_HD void normal_finish(const NormalArgs& a, long long bt, int x0, int tid, co
 
 #if defined(__CUDACC__)
 template <class P>
-__global__ void __launch_bounds__(P::NT, 3) normal_op_kernel(const NormalArgs a) {
+__global__ void __launch_bounds__(P::NT, 2) normal_op_kernel(const NormalArgs a) {
   extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
   cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);
   uint8_t* mrow = reinterpret_cast<uint8_t*>(smem + P::SMEM_ELEMS);
@@ -150,21 +157,23 @@ __global__ void __launch_bounds__(P::NT, 3) normal_op_kernel(const NormalArgs a)
   const long long bt = blockIdx.x / chunks;
   const int x0 = (blockIdx.x % chunks) * P::XC;
   for (int n = tid; n < P::H; n += P::NT) { smem[P::TW_OFF + n] = twiddle(n, P::H); mrow[n] = a.mask[bt * P::H + n]; }
+  normal_stage_x<P>(a, smem, bt, x0, tid);            // each thread only ever reads back its own rows
   float accr[P::G], acci[P::G];
+  cfloat sv[P::G];
 #pragma unroll
   for (int k = 0; k < P::G; ++k) { accr[k] = 0.f; acci[k] = 0.f; }
   const float scale = 1.f / (float)P::H;              // ortho forward * ortho inverse along h
   __syncthreads();
 #pragma unroll 1
   for (int c = 0; c < a.C; ++c) {
-    normal_step1<P>(a, smem, bt, c, x0, tid);
+    normal_step1<P>(a, smem, bt, c, x0, tid, sv);
     __syncthreads();
     for (int task = tid; task < P::TASKS2; task += P::NT) normal_step2<P>(smem, mrow, task);
     __syncthreads();
-    normal_step3<P>(a, smem, bt, c, x0, tid, accr, acci, scale);
+    normal_step3<P>(smem, tid, sv, accr, acci, scale);
     __syncthreads();
   }
-  normal_finish<P>(a, bt, x0, tid, accr, acci, *a.vptr);
+  normal_finish<P>(a, smem, bt, x0, tid, accr, acci, *a.vptr);
 }
 #endif
 
@@ -174,21 +183,23 @@ void normal_op_emulate(const NormalArgs& a, long long n_bt) {
   uint8_t* mrow = new uint8_t[P::H];
   float (*accr)[P::G] = new float[P::NT][P::G];
   float (*acci)[P::G] = new float[P::NT][P::G];
+  cfloat (*sv)[P::G] = new cfloat[P::NT][P::G];
   const int chunks = a.W / P::XC;
   for (long long blk = 0; blk < n_bt * chunks; ++blk) {
     const long long bt = blk / chunks;
     const int x0 = (int)(blk % chunks) * P::XC;
     for (int n = 0; n < P::H; ++n) { smem[P::TW_OFF + n] = twiddle(n, P::H); mrow[n] = a.mask[bt * P::H + n]; }
     for (int tid = 0; tid < P::NT; ++tid) for (int k = 0; k < P::G; ++k) { accr[tid][k] = 0.f; acci[tid][k] = 0.f; }
+    for (int tid = 0; tid < P::NT; ++tid) normal_stage_x<P>(a, smem, bt, x0, tid);
     for (int c = 0; c < a.C; ++c) {
-      for (int tid = 0; tid < P::NT; ++tid) normal_step1<P>(a, smem, bt, c, x0, tid);
+      for (int tid = 0; tid < P::NT; ++tid) normal_step1<P>(a, smem, bt, c, x0, tid, sv[tid]);
       for (int tid = 0; tid < P::NT; ++tid)
         for (int task = tid; task < P::TASKS2; task += P::NT) normal_step2<P>(smem, mrow, task);
-      for (int tid = 0; tid < P::NT; ++tid) normal_step3<P>(a, smem, bt, c, x0, tid, accr[tid], acci[tid], 1.f / (float)P::H);
+      for (int tid = 0; tid < P::NT; ++tid) normal_step3<P>(smem, tid, sv[tid], accr[tid], acci[tid], 1.f / (float)P::H);
     }
-    for (int tid = 0; tid < P::NT; ++tid) normal_finish<P>(a, bt, x0, tid, accr[tid], acci[tid], *a.vptr);
+    for (int tid = 0; tid < P::NT; ++tid) normal_finish<P>(a, smem, bt, x0, tid, accr[tid], acci[tid], *a.vptr);
   }
-  delete[] smem; delete[] mrow; delete[] accr; delete[] acci;
+  delete[] smem; delete[] mrow; delete[] accr; delete[] acci; delete[] sv;
 }
 
 }  // namespace b2s

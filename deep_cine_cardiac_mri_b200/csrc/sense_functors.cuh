@@ -157,7 +157,8 @@ template <int H, int W, bool INV> struct EpiPlain {
   cfloat* out; long long image_stride;
   struct Ctx { cfloat* p; };
   typedef cfloat* Ptr;
-  B2S_HD Ctx ctx(long long image) const { Ctx c; c.p = out + image * image_stride; return c; }
+  B2S_HD Ctx ctx(long long image, const uint8_t*) const { Ctx c; c.p = out + image * image_stride; return c; }
+  B2S_HD void stage_mask(long long, uint8_t*, int, int) const {}
   B2S_HD Ptr task_ptr(const Ctx& c, int m, int kx) const { return c.p + m * W + kx; }
   template <int G, int NC> struct Pre {};
   template <int G, int NC> B2S_HD void prefetch(Ptr, Pre<G, NC>&) const {}
@@ -176,18 +177,23 @@ template <int H, int W, bool INV> struct EpiPlain {
 // MODE 0: k ; 1: k*m + 0.0 ; 2: (1-m) k + m (k + v ref)/(1+v) ; 3: k*m - ref
 template <int H, int W, int MODE> struct EpiKspace {
   cfloat* out; const cfloat* ref; const uint8_t* mask; const float* vptr; int C; long long hw;
-  struct Ctx { cfloat* p; const cfloat* r; const uint8_t* m; float v; };
-  struct Ptr { cfloat* p; const cfloat* r; const uint8_t* m; float v; };
-  B2S_HD Ctx ctx(long long image) const {
+  struct Ctx { cfloat* p; const cfloat* r; const uint8_t* m; float v, inv1v; };
+  struct Ptr { cfloat* p; const cfloat* r; const uint8_t* m; float v, inv1v; };
+  // the (b,t) mask row of this item, staged once per item into shared memory (mrow)
+  B2S_HD void stage_mask(long long image, uint8_t* mrow, int tid, int nt) const {
+    if (MODE >= 1) { const uint8_t* src = mask + (image / C) * H; for (int y = tid; y < H; y += nt) mrow[y] = src[y]; }
+  }
+  B2S_HD Ctx ctx(long long image, const uint8_t* mrow) const {
     Ctx c; c.p = out + image * hw;
     c.r = (MODE >= 2) ? ref + image * hw : nullptr;
-    c.m = (MODE >= 1) ? mask + (image / C) * H : nullptr;
+    c.m = (MODE >= 1) ? mrow : nullptr;
     c.v = (MODE == 2) ? *vptr : 0.f;
+    c.inv1v = 1.f / (1.f + c.v);
     return c;
   }
   B2S_HD Ptr task_ptr(const Ctx& c, int m, int kx) const {
     Ptr t; const int off = m * W + kx;
-    t.p = c.p + off; t.r = (MODE >= 2) ? c.r + off : nullptr; t.m = (MODE >= 1) ? c.m + m : nullptr; t.v = c.v;
+    t.p = c.p + off; t.r = (MODE >= 2) ? c.r + off : nullptr; t.m = (MODE >= 1) ? c.m + m : nullptr; t.v = c.v; t.inv1v = c.inv1v;
     return t;
   }
   template <int G, int NC> struct Pre { cvec<NC> r[(MODE >= 2) ? G : 1]; unsigned mbits; };
@@ -215,7 +221,7 @@ template <int H, int W, int MODE> struct EpiKspace {
         const cvec<NC> r = pre.r[k];
 #pragma unroll
         for (int n = 0; n < NC; ++n)
-          o.v[n] = make_c((re_in[n] + t.v * r.v[n].x) / (1.f + t.v), (im_in[n] + t.v * r.v[n].y) / (1.f + t.v));
+          o.v[n] = make_c((re_in[n] + t.v * r.v[n].x) * t.inv1v, (im_in[n] + t.v * r.v[n].y) * t.inv1v);
       } else {
 #pragma unroll
         for (int n = 0; n < NC; ++n) o.v[n] = make_c(re_in[n], im_in[n]);
@@ -240,11 +246,12 @@ template <int H, int W> struct EpiReduce {
   long long os_b, os_t, os_c, ms_b, ms_t, ms_c;
   struct Ctx { cfloat* o; const cfloat* m; };
   struct Ptr { cfloat* o; const cfloat* m; };
-  B2S_HD Ctx ctx(long long image) const {
+  B2S_HD Ctx ctx(long long image, const uint8_t*) const {
     const long long c = image % C, bt = image / C, b = bt / T, t = bt % T;
     Ctx k; k.o = out + b * os_b + t * os_t + c * os_c; k.m = mult + b * ms_b + t * ms_t + c * ms_c;
     return k;
   }
+  B2S_HD void stage_mask(long long, uint8_t*, int, int) const {}
   B2S_HD Ptr task_ptr(const Ctx& c, int m, int kx) const { Ptr t; t.o = c.o + m * W + kx; t.m = c.m + m * W + kx; return t; }
   template <int G, int NC> struct Pre { cvec<NC> s[G]; };
   template <int G, int NC> B2S_HD void prefetch(const Ptr& t, Pre<G, NC>& pre) const {
