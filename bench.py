@@ -120,6 +120,10 @@ def cpu_reference_run(steps: int, warmup: int):
     from oracle import torch_port as T
     mk, mask = make_inputs(0, 1)
     mk, mask = torch.from_numpy(mk), torch.from_numpy(mask)
+    try:                                       # torchrun exports OMP_NUM_THREADS=1; the reference would use every core
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+    except Exception:
+        pass
     cores = torch.get_num_threads()
     with torch.no_grad():
         for _ in range(warmup):

@@ -9,12 +9,20 @@ using namespace b2s;
 
 namespace {
 
-typedef Plan<200, 200, 256, 1> P200;    // 8 warps x 255 registers, 64-bit global accesses
+typedef Plan<200, 200, 256, 1, 2> P200H;   // half split: 8 warps x 255 registers, 1 CTA/SM
+typedef Plan<200, 200, 128, 1, 4> P200Q;   // quarter split: 2 CTAs x 4 warps per SM
+typedef Plan<256, 256, 256, 1, 4> P256;    // quarter split, 1 CTA/SM
+
+static int use_quarter() {
+  static int q = -1;
+  if (q < 0) { const char* e = getenv("B2S_SPLIT"); q = (e && atoi(e) == 4) ? 1 : 0; }
+  return q;
+}
 
 template <class P, class Pro, class Epi, bool CARRY = false>
 int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st) {
   if (n_images <= 0) return B2S_OK;
-  if (2 * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
+  if (P::FOLD * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
   auto kern = fft2_half_kernel<P, Pro, Epi, CARRY>;
   int dev = 0, sms = 0;
   B2S_CUDA(cudaGetDevice(&dev));
@@ -27,17 +35,112 @@ int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, 
     B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<P>::SMEM_BYTES));
     configured[dev] = true;
   }
-  const int n_items = (int)(2 * n_images);
-  const unsigned grid = (unsigned)(n_items < sms ? n_items : sms);   // persistent: one CTA per SM
+  const int n_items = (int)(P::FOLD * n_images);
+  const int slots = sms * P::CTAS;
+  const unsigned grid = (unsigned)(n_items < slots ? n_items : slots);   // persistent: P::CTAS CTAs per SM
   static int stagger = -1;
   if (stagger < 0) { const char* e = getenv("B2S_STAGGER_NS"); stagger = e ? atoi(e) : 0; }
   kern<<<grid, P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale, n_items, (unsigned)stagger);
   return check_launch("fft2_half_kernel");
 }
 
+// Paired variant: clusters of two CTAs (one image per cluster at a time), see PhaseA2.
+template <class P, class Pro, class Epi, bool CARRY = false>
+int launch_pair(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st) {
+  if (n_images <= 0) return B2S_OK;
+  if (n_images > 0x3fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
+  auto kern = fft2_pair_kernel<P, Pro, Epi, CARRY>;
+  int dev = 0;
+  B2S_CUDA(cudaGetDevice(&dev));
+  static int sm_count[64] = {0};
+  static bool configured[64] = {false};
+  if (dev < 0 || dev >= 64) return fail(B2S_EUNSUPPORTED, "device index >= 64");
+  if (!sm_count[dev]) B2S_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+  if (!configured[dev]) {
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<P>::SMEM_BYTES));
+    configured[dev] = true;
+  }
+  const long long max_pairs = sm_count[dev] / 2;
+  const unsigned pairs = (unsigned)(n_images < max_pairs ? n_images : max_pairs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(P::NT); cfg.dynamicSmemBytes = Derived<P>::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const int n = (int)n_images;
+  B2S_CUDA(cudaLaunchKernelEx(&cfg, kern, pro, epi, scale, n));
+  return check_launch("fft2_pair_kernel");
+}
+
+// B2S_PAIR: unset/-1 = auto (paired kernel only where it measured faster: sens_expand without the DC
+// epilogue), 0 = never, 1 = always.  `auto_on` is the per-call-site default.
+static int use_pair(int auto_on = 0) {
+  static int p = -2;
+  if (p == -2) { const char* e = getenv("B2S_PAIR"); p = e ? atoi(e) : -1; }
+  return p < 0 ? auto_on : p;
+}
+
 }  // namespace
 
-extern "C" int b2s_has_fused_plan(int h, int w) { return (h == 200 && w == 200) ? 1 : 0; }
+// ---- per-plan launch helpers -------------------------------------------------------------------
+template <class P>
+int plan_fft2c(const float* in, float* out, int64_t n_images, int inverse, float scale, cudaStream_t st) {
+  constexpr int H = P::H, W = P::W;
+  const long long hw = (long long)H * W;
+  const float s = scale * centre_sign<P>();
+  if (inverse) {
+    ProPlain<H, W, true> pro{(const cfloat*)in, hw};
+    EpiPlain<H, W, true> epi{(cfloat*)out, hw};
+    if constexpr (P::FOLD == 2) { if (use_pair()) return launch_pair<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st); }
+    return launch_fused<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st);
+  }
+  ProPlain<H, W, false> pro{(const cfloat*)in, hw};
+  EpiPlain<H, W, false> epi{(cfloat*)out, hw};
+  if constexpr (P::FOLD == 2) { if (use_pair()) return launch_pair<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st); }
+  return launch_fused<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st);
+}
+
+template <class P>
+int plan_expand(const float* image, const float* sens, float* kspace, const float* ref, const uint8_t* mask,
+                const float* v, int mode, int t, int c, int64_t n, float scale, cudaStream_t st) {
+  constexpr int H = P::H, W = P::W;
+  const long long hw = (long long)H * W;
+  const float s = scale * centre_sign<P>();
+  ProExpand<H, W> pro{(const cfloat*)image, (const cfloat*)sens, t, c, hw};
+#define B2S_RUN(M)                                                                    \
+  {                                                                                   \
+    EpiKspace<H, W, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};      \
+    if constexpr (P::FOLD == 2) { if (use_pair(M != 2)) return launch_pair<P>(pro, epi, s, n, st); } \
+    return launch_fused<P>(pro, epi, s, n, st);                                       \
+  }
+  switch (mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) case 2: B2S_RUN(2) default: B2S_RUN(3) }
+#undef B2S_RUN
+}
+
+template <class P>
+int plan_reduce(const float* kspace, const float* mult, float* out, const uint8_t* mask, const float* v,
+                int weight_mode, int over_frames, int t, int c, int64_t n, float scale, cudaStream_t st) {
+  constexpr int H = P::H, W = P::W;
+  const long long hw = (long long)H * W;
+  const float s = scale * centre_sign<P>();
+  EpiReduce<H, W> epi;
+  epi.out = (cfloat*)out; epi.mult = (const cfloat*)mult; epi.T = t; epi.C = c;
+  if (!over_frames) { epi.os_b = t * hw; epi.os_t = hw; epi.os_c = 0; epi.ms_b = c * hw; epi.ms_t = 0; epi.ms_c = hw; }
+  else              { epi.os_b = c * hw; epi.os_t = 0; epi.os_c = hw; epi.ms_b = t * hw; epi.ms_t = hw; epi.ms_c = 0; }
+#define B2S_RUN(M)                                                      \
+  {                                                                     \
+    ProKspace<H, W, M> pro{(const cfloat*)kspace, mask, v, c, hw};      \
+    if constexpr (P::FOLD == 2) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
+    return launch_fused<P>(pro, epi, s, n, st);                         \
+  }
+  switch (weight_mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) default: B2S_RUN(2) }
+#undef B2S_RUN
+}
+
+static inline int plan_id(int h, int w) { return (h == 200 && w == 200) ? 1 : (h == 256 && w == 256) ? 2 : 0; }
+
+extern "C" int b2s_has_fused_plan(int h, int w) { return plan_id(h, w) ? 1 : 0; }
 
 extern "C" size_t b2s_scratch_bytes(int b, int t, int c, int h, int w) {
   if (b2s_has_fused_plan(h, w)) return 0;
@@ -51,19 +154,11 @@ extern "C" int b2s_fft2c(const float* in, float* out, int64_t n_images, int h, i
   if (!in || !out) return fail(B2S_EINVAL, "b2s_fft2c: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = norm_scale(h, w, inverse, norm);
-  if (h == 200 && w == 200) {
-    const long long hw = 40000;
-    const float s = scale * centre_sign<P200>();
-    if (inverse) {
-      ProPlain<200, 200, true> pro{(const cfloat*)in, hw};
-      EpiPlain<200, 200, true> epi{(cfloat*)out, hw};
-      return launch_fused<P200, ProPlain<200, 200, true>, EpiPlain<200, 200, true>, true>(pro, epi, s, n_images, st);
-    }
-    ProPlain<200, 200, false> pro{(const cfloat*)in, hw};
-    EpiPlain<200, 200, false> epi{(cfloat*)out, hw};
-    return launch_fused<P200, ProPlain<200, 200, false>, EpiPlain<200, 200, false>, true>(pro, epi, s, n_images, st);
+  switch (plan_id(h, w)) {
+    case 1: return use_quarter() ? plan_fft2c<P200Q>(in, out, n_images, inverse, scale, st) : plan_fft2c<P200H>(in, out, n_images, inverse, scale, st);
+    case 2: return plan_fft2c<P256>(in, out, n_images, inverse, scale, st);
+    default: return generic_fft2(in, out, n_images, h, w, inverse, scale, st);
   }
-  return generic_fft2(in, out, n_images, h, w, inverse, scale, st);
 }
 
 extern "C" int b2s_sens_expand(const float* image, const float* sens, float* kspace, const float* ref,
@@ -79,17 +174,11 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = (int64_t)b * t * c;
   const float scale = norm_scale(h, w, 0, norm);
-  if (h == 200 && w == 200) {
-    const long long hw = 40000;
-    const float s = scale * centre_sign<P200>();
-    ProExpand<200, 200> pro{(const cfloat*)image, (const cfloat*)sens, t, c, hw};
-#define B2S_RUN(M)                                                                            \
-  {                                                                                           \
-    EpiKspace<200, 200, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};            \
-    return launch_fused<P200>(pro, epi, s, n, st);                                          \
-  }
-    switch (mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) case 2: B2S_RUN(2) default: B2S_RUN(3) }
-#undef B2S_RUN
+  switch (plan_id(h, w)) {
+    case 1: return use_quarter() ? plan_expand<P200Q>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
+                                 : plan_expand<P200H>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
+    case 2: return plan_expand<P256>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
+    default: break;
   }
   // generic sizes: S*x -> kspace, FFT in place, epilogue in place
   int rc = launch_expand_product(image, sens, kspace, b, t, c, (int64_t)h * w, st);
@@ -114,22 +203,12 @@ extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* ou
   const int64_t hw = (int64_t)h * w;
   const float scale = norm_scale(h, w, 1, norm);
   const int64_t out_images = over_frames ? (int64_t)b * c : (int64_t)b * t;
-  if (out_images == 0) return B2S_OK;
-  if (h == 200 && w == 200) {
+  if (plan_id(h, w)) {
     B2S_CUDA(cudaMemsetAsync(out, 0, (size_t)out_images * hw * 2 * sizeof(float), st));
     if (n == 0) return B2S_OK;
-    const float s = scale * centre_sign<P200>();
-    EpiReduce<200, 200> epi;
-    epi.out = (cfloat*)out; epi.mult = (const cfloat*)mult; epi.T = t; epi.C = c;
-    if (!over_frames) { epi.os_b = t * hw; epi.os_t = hw; epi.os_c = 0; epi.ms_b = c * hw; epi.ms_t = 0; epi.ms_c = hw; }
-    else              { epi.os_b = c * hw; epi.os_t = 0; epi.os_c = hw; epi.ms_b = t * hw; epi.ms_t = hw; epi.ms_c = 0; }
-#define B2S_RUN(M)                                                            \
-  {                                                                           \
-    ProKspace<200, 200, M> pro{(const cfloat*)kspace, mask, v, c, hw};          \
-    return launch_fused<P200>(pro, epi, s, n, st);                          \
-  }
-    switch (weight_mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) default: B2S_RUN(2) }
-#undef B2S_RUN
+    if (plan_id(h, w) == 2) return plan_reduce<P256>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
+    return use_quarter() ? plan_reduce<P200Q>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
+                         : plan_reduce<P200H>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
   }
   // generic sizes: (row weight) -> IFFT into scratch -> conj-multiply + reduce
   const size_t need = (size_t)n * hw * 2 * sizeof(float);

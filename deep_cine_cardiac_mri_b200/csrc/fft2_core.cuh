@@ -52,10 +52,12 @@ B2S_HD cfloat twiddle(int n, int N) {
 // --------------------------------------------------------------------------- //
 // plans
 // --------------------------------------------------------------------------- //
-template <int H_, int W_, int NT_ = 256, int NC_ = 2> struct Plan;
+template <int H_, int W_, int NT_ = 256, int NC_ = 1, int FOLD_ = 2> struct Plan;
 
-// 200 x 200 (dataset crop, data/mri_data.py:273-277): h = 8*25, w = 5*40
-template <int NT_, int NC_> struct Plan<200, 200, NT_, NC_> {
+// 200 x 200 (dataset crop, data/mri_data.py:273-277): h = 8*25, w = 5*40.
+// FOLD 2: half split, 170 KB of shared memory, one 256-thread CTA per SM.
+// FOLD 4: quarter split, 85 KB, two 128-thread CTAs per SM (their phases overlap) at the price of 4x L2 reads.
+template <int NT_, int NC_, int FOLD_> struct Plan<200, 200, NT_, NC_, FOLD_> {
   static constexpr int H = 200, W = 200;
   static constexpr int G = 25;        // Phase C codelet size, H = 8*G
   static constexpr int R = 5;         // Phase A column radix, W = R*X0
@@ -64,21 +66,37 @@ template <int NT_, int NC_> struct Plan<200, 200, NT_, NC_> {
   static constexpr int PITCH = 213;   // row pitch of B (complex); 213 = 5 mod 16 keeps Phase B conflict-free
   static constexpr int NT = NT_;      // threads per CTA
   static constexpr int NC = NC_;      // adjacent columns per thread in Phases A and C (global access = 8*NC bytes)
+  static constexpr int FOLD = FOLD_;  // work items per image: item q produces output rows ky == q (mod FOLD)
+  static constexpr int CTAS = (FOLD_ == 4) ? 2 : 1;   // resident CTAs per SM
+};
+
+// 256 x 256 (BASELINE.json configs[4]): h = 8*32, w = 8*32.  Half an image (128 x 256 complex) does not fit
+// in shared memory, so the image is split in four: item q keeps 2 of the 8 radix-8 outputs (ky == q mod 4).
+template <int NT_, int NC_, int FOLD_> struct Plan<256, 256, NT_, NC_, FOLD_> {
+  static constexpr int H = 256, W = 256;
+  static constexpr int G = 32, R = 8, X0 = 32;
+  static constexpr int SEG = 33;      // 8 segments of 32 (+1 pad)
+  static constexpr int PITCH = 265;   // odd: lanes along rows stay conflict-free in Phase B
+  static constexpr int NT = NT_, NC = NC_;
+  static constexpr int FOLD = 4;
+  static constexpr int CTAS = 1;
+  static_assert(FOLD_ == 4, "256 x 256 only fits as a quarter split");
 };
 
 template <class P> struct Derived {
-  static constexpr int ROWS = 4 * P::G;                         // rows of B (half image)
+  static constexpr int NKEEP = 8 / P::FOLD;                     // radix-8 outputs (m-blocks) kept per item
+  static constexpr int ROWS = NKEEP * P::G;                     // rows of B
   static constexpr int SG = P::G & 1;                           // (-1)^(G j) relabel
   static constexpr int B_ELEMS = ROWS * P::PITCH;               // complex elements
   static constexpr int TW_OFF = B_ELEMS;                        // TW[W]
-  static constexpr int TH_OFF = TW_OFF + P::W;                  // TH[2][G][4] (both halves q)
-  static constexpr int SMEM_ELEMS = TH_OFF + 2 * P::G * 4;
+  static constexpr int TH_OFF = TW_OFF + P::W;                  // TH[FOLD][G][NKEEP] (every q)
+  static constexpr int SMEM_ELEMS = TH_OFF + 8 * P::G;
   static constexpr int MASK_BYTES = (P::H + 15) / 16 * 16;      // this item's mask row (uint8) after the tables
   static constexpr int SMEM_BYTES = SMEM_ELEMS * 8 + MASK_BYTES;
   static constexpr int XP = P::X0 / P::NC;                      // column groups per row group
   static constexpr int TASKS_A = P::G * XP;
   static constexpr int KXP = P::W / P::NC;
-  static constexpr int TASKS_C = 4 * KXP;
+  static constexpr int TASKS_C = NKEEP * KXP;
   static constexpr int RPR = (P::NT / P::R) < ROWS ? (P::NT / P::R) : ROWS;   // rows per Phase-B round
   static constexpr int ROUNDS_B = (ROWS + RPR - 1) / RPR;
   static_assert(P::H == 8 * P::G && P::W == P::R * P::X0, "bad plan");
@@ -87,8 +105,9 @@ template <class P> struct Derived {
   static_assert(P::R * P::SEG <= P::PITCH && P::W <= P::PITCH, "pitch too small");
 };
 
-// output row residue handled by m-block r of half q
-template <class P> B2S_HD int m_of(int r, int q) { return (2 * r + q + 4 * Derived<P>::SG) & 7; }
+// output row residue (mod 8) handled by m-block r of item q: radix-8 output m' = q + FOLD*r, relabelled by
+// the (-1)^(G j) part of the input checkerboard
+template <class P> B2S_HD int m_of(int r, int q) { return (P::FOLD * r + q + 4 * Derived<P>::SG) & 7; }
 
 // --------------------------------------------------------------------------- //
 // tables (per CTA, in shared memory)
@@ -96,8 +115,8 @@ template <class P> B2S_HD int m_of(int r, int q) { return (2 * r + q + 4 * Deriv
 template <class P> B2S_HD void build_tables(cfloat* smem, int tid, int nthreads) {
   using D = Derived<P>;
   for (int n = tid; n < P::W; n += nthreads) smem[D::TW_OFF + n] = twiddle(n, P::W);
-  for (int e = tid; e < 2 * P::G * 4; e += nthreads) {
-    const int q = e / (P::G * 4), g = (e >> 2) % P::G, r = e & 3;
+  for (int e = tid; e < 8 * P::G; e += nthreads) {
+    const int q = e / (P::G * D::NKEEP), g = (e / D::NKEEP) % P::G, r = e % D::NKEEP;
     cfloat t = twiddle(g * m_of<P>(r, q), P::H);
     if (g & 1) { t.x = -t.x; t.y = -t.y; }                      // (-1)^g of the input checkerboard
     smem[D::TH_OFF + e] = t;
@@ -119,8 +138,9 @@ template <class P, class Pro> struct PhaseA {
   static constexpr int G = P::G, R = P::R, X0 = P::X0, NC = P::NC, NT = P::NT;
   static constexpr int TPT = (D::TASKS_A + NT - 1) / NT;       // tasks per thread and item
   static constexpr int STEPS = TPT * R;
-  static constexpr int QD = Pro::QDEPTH;                        // steps in flight
-  static_assert(STEPS % QD == 0, "queue depth must divide the steps of an item");
+  static constexpr int NK = D::NKEEP;
+  static constexpr int QD = Pro::template qdepth<R>();          // steps in flight
+  static_assert(STEPS % QD == 0 && (2 * R) % QD == 0 && TPT % 2 == 0, "queue depth must divide two tasks' steps");
   typedef typename Pro::template Unit<NC> Unit;
   struct Queue { Unit u[QD]; };
 
@@ -146,13 +166,17 @@ template <class P, class Pro> struct PhaseA {
   static B2S_HD void run(const Pro& pro, const typename Pro::Ctx& ctx, const typename Pro::Ctx& next, bool has_next,
                          cfloat* smem, int q, int tid, Queue& qu) {
     const float h = 0.70710678118654752440f;
-    float ur[NC][4][R], ui[NC][4][R];       // [column][m-block r][column-group index i]
+    float ur[NC][NK][R], ui[NC][NK][R];     // [column][m-block r][column-group index i]
+#pragma unroll 1
+    for (int kp = 0; kp < TPT; kp += 2)     // two tasks per trip: queue slots stay compile-time, code stays small
 #pragma unroll
-    for (int s = 0; s < STEPS; ++s) {
-      const int k = s / R, i = s % R, slot = s % QD;
+    for (int u = 0; u < 2 * R; ++u) {
+      const int s = kp * R + u;
+      const int k = kp + u / R, i = u % R, slot = u % QD;
       int g, x0;
       const bool valid = task_of(tid, k, g, x0);
-      // ---- consume step s: fold the row pairs (j, j+4), W8 twiddles, radix-4 over j
+      // ---- consume step s: fold the row pairs (j, j+4), W8 twiddles, (pruned) radix-4 over j
+      const int q0 = q & 1;                   // parity of the kept radix-8 outputs
       float fr[NC][4], fi[NC][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -161,7 +185,7 @@ template <class P, class Pro> struct PhaseA {
         pro.template value<NC>(qu.u[slot], j + 4, br, bi);
 #pragma unroll
         for (int n = 0; n < NC; ++n) {
-          if (q == 0) {
+          if (q0 == 0) {
             fr[n][j] = ar[n] + br[n]; fi[n][j] = ai[n] + bi[n];
           } else {
             const float dr = ar[n] - br[n], di = ai[n] - bi[n];
@@ -174,18 +198,32 @@ template <class P, class Pro> struct PhaseA {
       }
 #pragma unroll
       for (int n = 0; n < NC; ++n) {
-        dft4(fr[n], fi[n]);
+        if (NK == 4) {                         // half split: all four outputs of this parity
+          dft4(fr[n], fi[n]);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { ur[n][r][i] = fr[n][r]; ui[n][r][i] = fi[n][r]; }
+          for (int r = 0; r < NK; ++r) { ur[n][r][i] = fr[n][r]; ui[n][r][i] = fi[n][r]; }
+        } else {                               // quarter split: radix-4 outputs q1 and q1 + 2 only
+          const int q1 = (q >> 1) & 1;
+          float hr[2], hi[2];
+          if (q1 == 0) {
+            hr[0] = fr[n][0] + fr[n][2]; hi[0] = fi[n][0] + fi[n][2];
+            hr[1] = fr[n][1] + fr[n][3]; hi[1] = fi[n][1] + fi[n][3];
+          } else {                             // (f_j - f_{j+2}) * w4^j, w4 = -i
+            hr[0] = fr[n][0] - fr[n][2]; hi[0] = fi[n][0] - fi[n][2];
+            hr[1] = fi[n][1] - fi[n][3]; hi[1] = -(fr[n][1] - fr[n][3]);
+          }
+          ur[n][0][i] = hr[0] + hr[1]; ui[n][0][i] = hi[0] + hi[1];
+          ur[n][NK - 1][i] = hr[0] - hr[1]; ui[n][NK - 1][i] = hi[0] - hi[1];
+        }
       }
       // ---- refill the slot with step s + QD (of this item, else of the next one)
       if (s + QD < STEPS) issue(pro, ctx, tid, s + QD, qu.u[slot]);
       else if (has_next) issue(pro, next, tid, s + QD - STEPS, qu.u[slot]);
       // ---- last column group of the task: row twiddles, radix-R over i, column twiddles, store
       if (i == R - 1 && valid) {
-        cfloat th[4];
+        cfloat th[NK];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) th[r] = smem[D::TH_OFF + (q * G + g) * 4 + r];
+        for (int r = 0; r < NK; ++r) th[r] = smem[D::TH_OFF + (q * G + g) * NK + r];
 #pragma unroll
         for (int n = 0; n < NC; ++n) {
           const int x = x0 + n;
@@ -194,7 +232,7 @@ template <class P, class Pro> struct PhaseA {
 #pragma unroll
           for (int k1 = 1; k1 < R; ++k1) tw[k1] = smem[D::TW_OFF + (x * k1) % P::W];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
+          for (int r = 0; r < NK; ++r) {
             const float tx = th[r].x * sx, ty = th[r].y * sx;
 #pragma unroll
             for (int ii = 0; ii < R; ++ii) {
@@ -209,6 +247,118 @@ template <class P, class Pro> struct PhaseA {
             for (int k1 = 1; k1 < R; ++k1) {
               const float a = ur[n][r][k1], b = ui[n][r][k1];
               dst[k1 * P::SEG] = make_c(a * tw[k1].x - b * tw[k1].y, a * tw[k1].y + b * tw[k1].x);
+            }
+          }
+        }
+      }
+    }
+  }
+};
+
+// --------------------------------------------------------------------------- //
+// Phase A, paired (2-CTA cluster, half split only).
+//
+// The two CTAs of a cluster work on the SAME image; CTA `rank` owns output parity q = rank (its B buffer,
+// Phases B and C are unchanged).  In Phase A each CTA loads only HALF of the columns (x0 in
+// [rank*X0/2, (rank+1)*X0/2)) of every row, so every input element - and for sens_expand every S*x
+// product - is fetched/computed once per image instead of once per half: the L2 -> SM ingest, which bounds
+// the unpaired kernel, is halved.  From its loads a thread forms the folds of BOTH parities
+// (a_j + a_{j+4} and (a_j - a_{j+4}) w8^j), finishes both, and stores parity `rank` into its own B and the
+// other parity into the partner's B through distributed shared memory (`remote` = the partner's buffer
+// mapped into this CTA's address space; plain generic stores).
+// --------------------------------------------------------------------------- //
+template <class P, class Pro> struct PhaseA2 {
+  using D = Derived<P>;
+  static constexpr int G = P::G, R = P::R, X0 = P::X0, NC = P::NC, NT = P::NT;
+  static_assert(P::FOLD == 2 && X0 % (2 * NC) == 0, "paired Phase A needs the half split");
+  static constexpr int XH = X0 / 2 / NC;                        // column groups per row group and CTA
+  static constexpr int TASKS = G * XH;
+  static constexpr int TPT = (TASKS + NT - 1) / NT;
+  static constexpr int STEPS = TPT * R;
+  static constexpr int QD = Pro::template qdepth<R>();
+  static_assert(STEPS % QD == 0 && (2 * R) % QD == 0 && TPT % 2 == 0, "queue depth must divide two tasks' steps");
+  typedef typename Pro::template Unit<NC> Unit;
+  struct Queue { Unit u[QD]; };
+
+  static B2S_HD bool task_of(int tid, int k, int rank, int& g, int& x0) {
+    const int task = tid + k * NT;
+    g = task / XH; x0 = (rank * XH + (task - g * XH)) * NC;
+    return task < TASKS;
+  }
+  static B2S_HD void issue(const Pro& pro, const typename Pro::Ctx& ctx, int tid, int rank, int s, Unit& u) {
+    int g, x0;
+    if (!task_of(tid, s / R, rank, g, x0)) return;
+    pro.template fetch<NC, G * P::W>(ctx, g, g * P::W + x0 + X0 * (s % R), u);
+  }
+  static B2S_HD void prefill(const Pro& pro, const typename Pro::Ctx& ctx, int tid, int rank, Queue& q) {
+#pragma unroll
+    for (int s = 0; s < QD; ++s) issue(pro, ctx, tid, rank, s, q.u[s]);
+  }
+
+  // `own` = this CTA's shared memory (tables + B of parity `rank`), `remote` = the partner's B
+  static B2S_HD void run(const Pro& pro, const typename Pro::Ctx& ctx, const typename Pro::Ctx& next, bool has_next,
+                         cfloat* own, cfloat* remote, int rank, int tid, Queue& qu) {
+    const float h = 0.70710678118654752440f;
+    float ur[2][NC][4][R], ui[2][NC][4][R];   // [parity][column][m-block r][column-group index i]
+#pragma unroll 1
+    for (int kp = 0; kp < TPT; kp += 2)
+#pragma unroll
+    for (int u = 0; u < 2 * R; ++u) {
+      const int s = kp * R + u;
+      const int k = kp + u / R, i = u % R, slot = u % QD;
+      int g, x0;
+      const bool valid = task_of(tid, k, rank, g, x0);
+#pragma unroll
+      for (int n = 0; n < NC; ++n) {
+        float er[4], ei[4], orr[4], oi[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float ar[NC], ai[NC], br[NC], bi[NC];
+          pro.template value<NC>(qu.u[slot], j, ar, ai);
+          pro.template value<NC>(qu.u[slot], j + 4, br, bi);
+          er[j] = ar[n] + br[n]; ei[j] = ai[n] + bi[n];
+          const float dr = ar[n] - br[n], di = ai[n] - bi[n];
+          if (j == 0)      { orr[j] = dr;              oi[j] = di; }
+          else if (j == 1) { orr[j] = (dr + di) * h;   oi[j] = (di - dr) * h; }
+          else if (j == 2) { orr[j] = di;              oi[j] = -dr; }
+          else             { orr[j] = (di - dr) * h;   oi[j] = -(dr + di) * h; }
+        }
+        dft4(er, ei);
+        dft4(orr, oi);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { ur[0][n][r][i] = er[r]; ui[0][n][r][i] = ei[r]; ur[1][n][r][i] = orr[r]; ui[1][n][r][i] = oi[r]; }
+      }
+      if (s + QD < STEPS) issue(pro, ctx, tid, rank, s + QD, qu.u[slot]);
+      else if (has_next) issue(pro, next, tid, rank, s + QD - STEPS, qu.u[slot]);
+      if (i == R - 1 && valid) {
+#pragma unroll
+        for (int n = 0; n < NC; ++n) {
+          const int x = x0 + n;
+          const float sx = (x & 1) ? -1.f : 1.f;
+          cfloat tw[R];
+#pragma unroll
+          for (int k1 = 1; k1 < R; ++k1) tw[k1] = own[D::TW_OFF + (x * k1) % P::W];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            cfloat* base = (q == rank) ? own : remote;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const cfloat th = own[D::TH_OFF + (q * G + g) * 4 + r];
+              const float tx = th.x * sx, ty = th.y * sx;
+#pragma unroll
+              for (int ii = 0; ii < R; ++ii) {
+                const float a = ur[q][n][r][ii], b = ui[q][n][r][ii];
+                ur[q][n][r][ii] = a * tx - b * ty;
+                ui[q][n][r][ii] = a * ty + b * tx;
+              }
+              Dft<R>::run(ur[q][n][r], ui[q][n][r]);
+              cfloat* dst = base + (r * G + g) * P::PITCH + x;
+              dst[0] = make_c(ur[q][n][r][0], ui[q][n][r][0]);
+#pragma unroll
+              for (int k1 = 1; k1 < R; ++k1) {
+                const float a = ur[q][n][r][k1], b = ui[q][n][r][k1];
+                dst[k1 * P::SEG] = make_c(a * tw[k1].x - b * tw[k1].y, a * tw[k1].y + b * tw[k1].x);
+              }
             }
           }
         }

@@ -6,8 +6,10 @@
 #include "fft2_kernel.cuh"
 
 using namespace b2s;
-typedef Plan<200, 200, 256, 1> P200;
-typedef Plan<200, 200, 256, 2> P200V;   // the 128-bit variant is emulated too
+typedef Plan<200, 200, 256, 1, 2> P200;    // half split
+typedef Plan<200, 200, 256, 2, 2> P200V;   // half split, 128-bit accesses
+typedef Plan<200, 200, 128, 1, 4> P200Q;   // quarter split (2 CTAs/SM on the device)
+typedef Plan<256, 256, 256, 1, 4> P256;
 
 static float norm_scale(int h, int w, int inverse, int norm) {
   // norm: 0 "backward", 1 "ortho", 2 "forward" (torch.fft semantics)
@@ -18,48 +20,46 @@ static float norm_scale(int h, int w, int inverse, int norm) {
   return (float)s;
 }
 
-static int g_variant = 0;   // 0: 64-bit accesses (NC=1), 1: 128-bit accesses (NC=2)
-#define EMU(PRO, EPI, SCALE, N) do { if (g_variant) fft2_half_emulate<P200V>(PRO, EPI, SCALE, N); else fft2_half_emulate<P200>(PRO, EPI, SCALE, N); } while (0)
+static int g_variant = 0;   // 200x200: 0 half split, 1 half split with 128-bit accesses, 2 quarter split, 3 paired (cluster)
+#define EMULATE(P, pro, epi, scale, n) do { if (g_variant == 3 && P::FOLD == 2 && P::NC == 1) fft2_pair_emulate_if<P>(pro, epi, scale, n); else fft2_half_emulate<P>(pro, epi, scale, n); } while (0)
+template <class P, class Pro, class Epi> static void fft2_pair_emulate_if(const Pro& pro, const Epi& epi, float scale, long long n) {
+  if constexpr (P::FOLD == 2 && P::NC == 1) fft2_pair_emulate<P>(pro, epi, scale, n); else fft2_half_emulate<P>(pro, epi, scale, n);
+}
 
-extern "C" {
-
-void emu_set_variant(int v) { g_variant = v; }
-
-int emu_fft2c(const float* in, float* out, long long n_images, int h, int w, int inverse, int norm) {
-  if (h != 200 || w != 200) return 2;
-  const float scale = norm_scale(h, w, inverse, norm) * centre_sign<P200>();
-  const long long hw = (long long)h * w;
+template <class P> static int t_fft2c(const float* in, float* out, long long n_images, int inverse, int norm) {
+  constexpr int H = P::H, W = P::W;
+  const float scale = norm_scale(H, W, inverse, norm) * centre_sign<P>();
+  const long long hw = (long long)H * W;
   if (inverse) {
-    ProPlain<200, 200, true> pro{(const cfloat*)in, hw};
-    EpiPlain<200, 200, true> epi{(cfloat*)out, hw};
-    EMU(pro, epi, scale, n_images);
+    ProPlain<H, W, true> pro{(const cfloat*)in, hw};
+    EpiPlain<H, W, true> epi{(cfloat*)out, hw};
+    EMULATE(P, pro, epi, scale, n_images);
   } else {
-    ProPlain<200, 200, false> pro{(const cfloat*)in, hw};
-    EpiPlain<200, 200, false> epi{(cfloat*)out, hw};
-    EMU(pro, epi, scale, n_images);
+    ProPlain<H, W, false> pro{(const cfloat*)in, hw};
+    EpiPlain<H, W, false> epi{(cfloat*)out, hw};
+    EMULATE(P, pro, epi, scale, n_images);
   }
   return 0;
 }
 
-int emu_sens_expand(const float* img, const float* sens, float* kout, const float* ref, const uint8_t* mask,
-                    const float* v, int mode, int b, int t, int c, int h, int w, int norm) {
-  if (h != 200 || w != 200) return 2;
-  const float scale = norm_scale(h, w, 0, norm) * centre_sign<P200>();
-  const long long hw = (long long)h * w, n = (long long)b * t * c;
-  ProExpand<200, 200> pro{(const cfloat*)img, (const cfloat*)sens, t, c, hw};
-#define RUN(M) { EpiKspace<200, 200, M> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, hw}; \
-                 EMU(pro, epi, scale, n); }
+template <class P> static int t_expand(const float* img, const float* sens, float* kout, const float* ref, const uint8_t* mask,
+                                       const float* v, int mode, int b, int t, int c, int norm) {
+  constexpr int H = P::H, W = P::W;
+  const float scale = norm_scale(H, W, 0, norm) * centre_sign<P>();
+  const long long hw = (long long)H * W, n = (long long)b * t * c;
+  ProExpand<H, W> pro{(const cfloat*)img, (const cfloat*)sens, t, c, hw};
+#define RUN(M) { EpiKspace<H, W, M> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, hw}; EMULATE(P, pro, epi, scale, n); }
   if (mode == 0) RUN(0) else if (mode == 1) RUN(1) else if (mode == 2) RUN(2) else if (mode == 3) RUN(3) else return 1;
 #undef RUN
   return 0;
 }
 
-int emu_sens_reduce(const float* k, const float* mult, float* out, const uint8_t* mask, const float* v, int wmode,
-                    int over_frames, int b, int t, int c, int h, int w, int norm) {
-  if (h != 200 || w != 200) return 2;
-  const float scale = norm_scale(h, w, 1, norm) * centre_sign<P200>();
-  const long long hw = (long long)h * w, n = (long long)b * t * c;
-  EpiReduce<200, 200> epi;
+template <class P> static int t_reduce(const float* k, const float* mult, float* out, const uint8_t* mask, const float* v, int wmode,
+                                       int over_frames, int b, int t, int c, int norm) {
+  constexpr int H = P::H, W = P::W;
+  const float scale = norm_scale(H, W, 1, norm) * centre_sign<P>();
+  const long long hw = (long long)H * W, n = (long long)b * t * c;
+  EpiReduce<H, W> epi;
   epi.out = (cfloat*)out; epi.mult = (const cfloat*)mult; epi.T = t; epi.C = c;
   if (!over_frames) {   // out (b,t,h,w) = sum_c conj(S[b,c]) y[b,t,c]
     epi.os_b = t * hw; epi.os_t = hw; epi.os_c = 0; epi.ms_b = c * hw; epi.ms_t = 0; epi.ms_c = hw;
@@ -68,10 +68,33 @@ int emu_sens_reduce(const float* k, const float* mult, float* out, const uint8_t
     epi.os_b = c * hw; epi.os_t = 0; epi.os_c = hw; epi.ms_b = t * hw; epi.ms_t = hw; epi.ms_c = 0;
     for (long long i = 0; i < (long long)b * c * hw * 2; ++i) out[i] = 0.f;
   }
-#define RUN(M) { ProKspace<200, 200, M> pro{(const cfloat*)k, mask, v, c, hw}; EMU(pro, epi, scale, n); }
+#define RUN(M) { ProKspace<H, W, M> pro{(const cfloat*)k, mask, v, c, hw}; EMULATE(P, pro, epi, scale, n); }
   if (wmode == 0) RUN(0) else if (wmode == 1) RUN(1) else if (wmode == 2) RUN(2) else return 1;
 #undef RUN
   return 0;
+}
+
+#define DISPATCH(FN, ...)                                                          \
+  if (h == 200 && w == 200) return g_variant == 2 ? FN<P200Q>(__VA_ARGS__) : g_variant == 1 ? FN<P200V>(__VA_ARGS__) : FN<P200>(__VA_ARGS__); \
+  if (h == 256 && w == 256) return FN<P256>(__VA_ARGS__);                          \
+  return 2;
+
+extern "C" {
+
+void emu_set_variant(int v) { g_variant = v; }
+
+int emu_fft2c(const float* in, float* out, long long n_images, int h, int w, int inverse, int norm) {
+  DISPATCH(t_fft2c, in, out, n_images, inverse, norm)
+}
+
+int emu_sens_expand(const float* img, const float* sens, float* kout, const float* ref, const uint8_t* mask,
+                    const float* v, int mode, int b, int t, int c, int h, int w, int norm) {
+  DISPATCH(t_expand, img, sens, kout, ref, mask, v, mode, b, t, c, norm)
+}
+
+int emu_sens_reduce(const float* k, const float* mult, float* out, const uint8_t* mask, const float* v, int wmode,
+                    int over_frames, int b, int t, int c, int h, int w, int norm) {
+  DISPATCH(t_reduce, k, mult, out, mask, v, wmode, over_frames, b, t, c, norm)
 }
 
 }  // extern "C"

@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/b200sense.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.SIGNATURES"
     assert lib.b2s_version() >= 100
-    assert lib.b2s_has_fused_plan(200, 200) == 1 and lib.b2s_has_fused_plan(256, 256) == 0
+    assert lib.b2s_has_fused_plan(200, 200) == 1 and lib.b2s_has_fused_plan(256, 256) == 1 and lib.b2s_has_fused_plan(192, 192) == 0
     assert lib.b2s_scratch_bytes(1, 2, 3, 200, 200) == 0
     assert lib.b2s_scratch_bytes(1, 2, 3, 8, 6) == 2 * 3 * 8 * 6 * 8
 
@@ -95,22 +95,22 @@ def test_generated_codelets(emu):
     assert emu.emu_codelet_worst_error() <= 2e-7          # dft2 ... dft40 vs a direct double DFT
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-def test_emulated_fft2c(emu, variant):
+@pytest.mark.parametrize("variant,hw", [(0, 200), (1, 200), (2, 200), (3, 200), (0, 256)])
+def test_emulated_fft2c(emu, variant, hw):
     emu.emu_set_variant(variant)
-    x = G.rng_normal(1, (2, 200, 200, 2))
+    x = G.rng_normal(1, (2, hw, hw, 2))
     for inv, norm, nn in ((0, 1, "ortho"), (1, 1, "ortho"), (0, 0, None), (1, 2, "forward")):
         out = np.empty_like(x)
-        assert emu.emu_fft2c(P(x), P(out), ctypes.c_longlong(2), 200, 200, inv, norm) == 0
+        assert emu.emu_fft2c(P(x), P(out), ctypes.c_longlong(2), hw, hw, inv, norm) == 0
         ref = (O.ifft2c if inv else O.fft2c)(x.astype(np.float64), norm=nn)
         assert rel(out, ref) <= 1e-6
     assert emu.emu_fft2c(P(x), P(x), ctypes.c_longlong(1), 128, 128, 0, 1) == 2     # no plan -> EUNSUPPORTED
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-def test_emulated_sense_operators(emu, variant):
+@pytest.mark.parametrize("variant,hw", [(0, 200), (1, 200), (2, 200), (3, 200), (0, 256)])
+def test_emulated_sense_operators(emu, variant, hw):
     emu.emu_set_variant(variant)
-    b, t, c, h, w = 2, 2, 3, 200, 200
+    b, t, c, h, w = 2, 2, 3, hw, hw
     cs = G.sense_case(5, b, t, c, h, w)
     d = {k: (a.astype(np.float64) if getattr(a, "dtype", None) == np.float32 and a.ndim else a) for k, a in cs.items()}
     v = np.array([O.softplus(cs["lam"])], dtype=np.float32)

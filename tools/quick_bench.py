@@ -41,7 +41,8 @@ def main():
         img = ops.raw_sens_reduce(ks[j], s)
         return ops.raw_sens_expand(img, s, 2, refs[j], m, v)
     res["dc_step"] = (timeit(dc_step), 3 * K + 2 * S + 2 * I)
-    res["normal_op"] = (timeit(lambda: ops.raw_normal_op(x, s, m, v)), 2 * I + S)
+    if ops.normal_op_supported(h, w):
+        res["normal_op"] = (timeit(lambda: ops.raw_normal_op(x, s, m, v)), 2 * I + S)
     res["dc_blend"] = (timeit(lambda: ops.raw_dc_blend(ks[nxt()], refs[i[0]], m, v)), 3 * K)
     big = torch.empty(1 << 28, dtype=torch.float32, device=dev)
     big2 = torch.empty_like(big)
