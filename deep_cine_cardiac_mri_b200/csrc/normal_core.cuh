@@ -148,7 +148,7 @@ B2S_HD void normal_finish(const NormalArgs& a, const cfloat* smem, long long bt,
 
 #if defined(__CUDACC__)
 template <class P>
-__global__ void __launch_bounds__(P::NT, 2) normal_op_kernel(const NormalArgs a) {
+__global__ void __launch_bounds__(P::NT, 3) normal_op_kernel(const NormalArgs a) {
   extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
   cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);
   uint8_t* mrow = reinterpret_cast<uint8_t*>(smem + P::SMEM_ELEMS);
