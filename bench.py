@@ -257,6 +257,23 @@ def run_ours(args, rank, world, local):
         torch.cuda.synchronize()
         img_sec = bdist.max_over_ranks(f0.elapsed_time(f1) * 1e-3, dev)
 
+        # ---- BASELINE configs[2] shape: CineNet (CRNN) SENSE/CG hot path, 10 iterations x CG 4, 20 coils, 25 frames
+        from deep_cine_cardiac_mri_b200 import synth
+        ccase = synth.cine_case(5000 + rank, 1, 25, 20, CFG["h"], CFG["w"])
+        cmk, cmask, csens = (torch.from_numpy(ccase[k]).to(dev) for k in ("masked_kspace", "mask", "sens"))
+        for _ in range(2):
+            pipeline.cinenet_hot_path(cmk, cmask, csens, v, 10, 4)
+        torch.cuda.synchronize()
+        bdist.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_cine = max(4, K // 4)
+        c0.record()
+        for _ in range(n_cine):
+            pipeline.cinenet_hot_path(cmk, cmask, csens, v, 10, 4)
+        c1.record()
+        torch.cuda.synchronize()
+        cine_sec = bdist.max_over_ranks(c0.elapsed_time(c1) * 1e-3, dev)
+
     if rank != 0:
         return
     peak, peak_src = load_peaks()
@@ -281,6 +298,9 @@ def run_ours(args, rank, world, local):
                      "algorithmic_bytes_per_launch": alg["sens_expand_dc"], "us_per_launch": dom_sec * 1e6,
                      "launches_timed": len(dom_ms), "peak_source": peak_src},
         "cpu_baseline": cpu,
+        "cinenet_hot_path": {"value": world * n_cine / cine_sec, "unit": UNIT, "ms_per_slice": cine_sec / n_cine * 1e3,
+                             "workload": "CineNet SENSE/CG hot path, 10 iterations x CG 4 (50 normal-operator applications), "
+                                         "20-coil 25-frame 200x200, b=1 per call, regulariser = identity"},
         "image_domain_variant": {"value": world * nb * K / img_sec, "unit": UNIT, "ms_per_step": img_sec / K * 1e3,
                                  "note": "identical outputs; each cascade = one on-chip normal-operator launch "
                                          "(A^H DC A x = ssq x - eta (A^H M A x - A^H ref)); not the headline"},

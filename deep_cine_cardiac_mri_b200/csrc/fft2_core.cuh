@@ -275,7 +275,7 @@ template <class P, class Pro> struct PhaseA2 {
   static constexpr int TASKS = G * XH;
   static constexpr int TPT = (TASKS + NT - 1) / NT;
   static constexpr int STEPS = TPT * R;
-  static constexpr int QD = Pro::template qdepth<R>();
+  static constexpr int QD = Pro::template qdepth<R, true>();
   static_assert(STEPS % QD == 0 && (2 * R) % QD == 0 && TPT % 2 == 0, "queue depth must divide two tasks' steps");
   typedef typename Pro::template Unit<NC> Unit;
   struct Queue { Unit u[QD]; };

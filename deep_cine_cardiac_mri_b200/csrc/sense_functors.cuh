@@ -71,7 +71,8 @@ template <int H, int W, bool INV> struct ProPlain {
   struct Ctx { const cfloat* p; };
   typedef const cfloat* Ptr;
   B2S_HD Ctx ctx(long long image) const { Ctx c; c.p = in + image * image_stride; return c; }
-  template <int R> static constexpr int qdepth() { return R <= 5 ? R : R / 2; }   // ~one task (32-40 loads) in flight per thread
+  // ~one task (32-40 loads) in flight per thread; the paired kernel holds both parities, so it keeps fewer
+  template <int R, bool PAIRED = false> static constexpr int qdepth() { return PAIRED ? 2 : (R <= 5 ? R : R / 2); }
   template <int NC> struct Unit { cvec<NC> a[8]; };
   // raw loads of the 8 rows g + G*j of one column group (row stride RS = G*W elements)
   template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int, int off, Unit<NC>& u) const {
@@ -101,7 +102,7 @@ template <int H, int W> struct ProExpand {
     const long long c = image % C, bt = image / C, b = bt / T;
     Ctx k; k.a = img + bt * hw; k.s = sens + (b * C + c) * hw; return k;
   }
-  template <int R> static constexpr int qdepth() { return 2; }                    // 2 x 16 loads in flight per thread
+  template <int R, bool PAIRED = false> static constexpr int qdepth() { return PAIRED ? 1 : 2; }   // x 16 loads in flight per thread
   template <int NC> struct Unit { cvec<NC> a[8], s[8]; };
   template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int, int off, Unit<NC>& u) const {
     const cfloat* pa = c.a + off; const cfloat* ps = c.s + off;
@@ -131,7 +132,7 @@ template <int H, int W, int WMODE> struct ProKspace {
     if (WMODE == 2) { const float v = *vptr; c.wb = -v / (1.f + v); }
     return c;
   }
-  template <int R> static constexpr int qdepth() { return R <= 5 ? R : R / 2; }
+  template <int R, bool PAIRED = false> static constexpr int qdepth() { return PAIRED ? 2 : (R <= 5 ? R : R / 2); }
   template <int NC> struct Unit { cvec<NC> a[8]; float w[WMODE ? 8 : 1]; };
   template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int g, int off, Unit<NC>& u) const {
     const cfloat* p = c.p + off;

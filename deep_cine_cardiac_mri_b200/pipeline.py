@@ -80,6 +80,26 @@ def varnet_hot_path_image_domain(masked_kspace: torch.Tensor, mask: torch.Tensor
     return F.complex_abs(img)
 
 
+def cinenet_hot_path(masked_kspace: torch.Tensor, mask: torch.Tensor, sens_maps: torch.Tensor,
+                     v: Union[float, torch.Tensor] = 1.0, n_cascades: int = 10, cg_iters: int = 4,
+                     regulariser: Optional[Callable] = None) -> torch.Tensor:
+    """SENSE/CG hot path of a CineNet / CineNet_RNN forward (models/cinenet.py:61-73, 222-257;
+    recurrent_cinenet.py:127-187): x_ref = A^H y, then per cascade [regulariser] and `cg_iters` steps of CG on
+    (A^H M A + v) x = x_ref + v x_reg.  Every H application is one on-chip normal-operator launch and the CG
+    scalars stay on the device (the reference does 3 `.item()` host syncs per iteration).  b == 1 per call keeps
+    the reference's semantics (its dot products span the whole batch, cinenet.py:148).  Returns (b,t,h,w)."""
+    from . import blocks
+    b, t, c, h, w, _ = masked_kspace.shape
+    vd = v.detach().reshape(1) if isinstance(v, torch.Tensor) else ops._vdev(v, masked_kspace.device)
+    x_ref = ops.sens_reduce(masked_kspace, sens_maps)                        # (b,t,h,w,2)
+    x = x_ref
+    for _ in range(n_cascades):
+        model_out = x if regulariser is None else regulariser(x.unsqueeze(2)).squeeze(2).contiguous()
+        rhs = ops.raw_axpby(ops._f32c(x_ref), ops._f32c(model_out), vd, 1.0)  # x_ref + v * model_out
+        x = blocks._cg_inference(model_out, rhs, mask, sens_maps, vd, cg_iters)
+    return F.complex_abs(x)
+
+
 def hot_path_algorithmic_bytes(b: int, t: int, c: int, h: int, w: int, n_cascades: int) -> dict:
     """Algorithmic HBM bytes of the calls above, fp32."""
     K, I, S = b * t * c * h * w * 8, b * t * h * w * 8, b * c * h * w * 8

@@ -220,6 +220,23 @@ def test_whole_hot_path_and_image_domain_variant(ops):
             assert O.ssim(want[i], g[i]) >= 1 - 1e-6
 
 
+def test_cinenet_hot_path(ops):
+    """pipeline.cinenet_hot_path == oracle chain of conj_grad blocks (cinenet.py:61-73, 136-171, 222-257)."""
+    from deep_cine_cardiac_mri_b200 import pipeline, synth
+    b, t, c, h, w = 1, 4, 5, 200, 200
+    case = synth.cine_case(21, b, t, c, h, w)
+    mk, mask, sens = cu(case["masked_kspace"]), cu(case["mask"]), cu(case["sens"])
+    v, n_casc, iters = 0.6, 3, 4
+    with torch.no_grad():
+        got = pipeline.cinenet_hot_path(mk, mask, sens, v, n_casc, iters)
+    mk64, s64 = f64(case["masked_kspace"]), f64(case["sens"])
+    x_ref = O.sens_reduce(mk64, s64)
+    x = x_ref
+    for _ in range(n_casc):
+        x = O.conj_grad(x, x_ref + v * x, case["mask"], s64, v, iters)
+    assert rel(got, O.complex_abs(x[:, :, 0])) <= 5e-5
+
+
 # ------------------------------- golden fixtures ---------------------------- #
 GOLD = np.load(G.HERE / "golden_v1.npz")
 
