@@ -100,6 +100,30 @@ def cinenet_hot_path(masked_kspace: torch.Tensor, mask: torch.Tensor, sens_maps:
     return F.complex_abs(x)
 
 
+class Graphed:
+    """CUDA-graph capture of a hot-path call with static input buffers.
+
+    Nothing on the path synchronises with the host (device-side ACS window, device-side CG scalars, `v` read from
+    device memory), so a whole forward is capturable: `g = Graphed(varnet_hot_path, mk, mask, v, 12)`, then
+    `g.inputs[0].copy_(new_kspace); out = g()` replays every kernel with one launch."""
+
+    def __init__(self, fn: Callable, *args, warmup: int = 2, **kwargs):
+        self.inputs = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream), torch.no_grad():
+            for _ in range(warmup):                       # plans / function attributes / scratch are set up here
+                fn(*self.inputs, **kwargs)
+        torch.cuda.current_stream().wait_stream(stream)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.output = fn(*self.inputs, **kwargs)
+
+    def __call__(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.output
+
+
 def hot_path_algorithmic_bytes(b: int, t: int, c: int, h: int, w: int, n_cascades: int) -> dict:
     """Algorithmic HBM bytes of the calls above, fp32."""
     K, I, S = b * t * c * h * w * 8, b * t * h * w * 8, b * c * h * w * 8

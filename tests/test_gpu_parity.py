@@ -237,6 +237,27 @@ def test_cinenet_hot_path(ops):
     assert rel(got, O.complex_abs(x[:, :, 0])) <= 5e-5
 
 
+def test_cuda_graph_capture_of_whole_hot_paths(ops):
+    """No host sync anywhere on the path: VarNet and CineNet hot paths capture into a CUDA graph and replay."""
+    from deep_cine_cardiac_mri_b200 import pipeline, synth
+    case = synth.cine_case(31, 1, 6, 4, 200, 200)
+    mk, mask, sens = cu(case["masked_kspace"]), cu(case["mask"]), cu(case["sens"])
+    v = torch.tensor([0.9], device="cuda")
+    with torch.no_grad():
+        eager_v = pipeline.varnet_hot_path(mk, mask, v, 3)
+        eager_c = pipeline.cinenet_hot_path(mk, mask, sens, v, 2, 3)
+    gv = pipeline.Graphed(pipeline.varnet_hot_path, mk, mask, v, 3)
+    gc = pipeline.Graphed(pipeline.cinenet_hot_path, mk, mask, sens, v, 2, 3)
+    assert float((gv() - eager_v).abs().max()) <= 1e-6 * float(eager_v.abs().max())
+    assert float((gc() - eager_c).abs().max()) <= 1e-6 * float(eager_c.abs().max())
+    # new data through the static input buffer
+    case2 = synth.cine_case(32, 1, 6, 4, 200, 200)
+    gv.inputs[0].copy_(cu(case2["masked_kspace"])); gv.inputs[1].copy_(cu(case2["mask"]))
+    with torch.no_grad():
+        want = pipeline.varnet_hot_path(cu(case2["masked_kspace"]), cu(case2["mask"]), v, 3)
+    assert float((gv() - want).abs().max()) <= 1e-6 * float(want.abs().max())
+
+
 # ------------------------------- golden fixtures ---------------------------- #
 GOLD = np.load(G.HERE / "golden_v1.npz")
 
