@@ -57,6 +57,16 @@ def test_abi_rejects_bad_arguments_without_a_gpu():
         _lib.check(3, "x")
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """gcc -std=c99 compiles a client of include/b200sense.h and links the shared library (C ABI, no C++/torch types)."""
+    from deep_cine_cardiac_mri_b200 import _lib
+    exe = tmp_path / "test_abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "tests" / "abi_c" / "test_abi.c"),
+                    "-L", str(_lib.LIB_PATH.parent), "-lb2sense", f"-Wl,-rpath,{_lib.LIB_PATH.parent}", "-o", str(exe)], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith("OK"), res.stdout + res.stderr
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from deep_cine_cardiac_mri_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)

@@ -258,6 +258,73 @@ def test_cuda_graph_capture_of_whole_hot_paths(ops):
     assert float((gv() - want).abs().max()) <= 1e-6 * float(want.abs().max())
 
 
+def test_block_dropins_with_identity_regularisers(ops):
+    """The remaining block-tier methods (blocks.py) against the oracle, with stand-in `self` objects."""
+    import types
+    from deep_cine_cardiac_mri_b200 import blocks
+    cs, d = make_case("a")
+    b, t, c, h, w = CASES["a"]
+    img, k, ref, sens, mask = (cu(cs[n]) for n in ("img", "k", "ref", "sens", "mask"))
+    lam = torch.tensor([float(cs["lam"])], device="cuda")
+    v = float(O.softplus(cs["lam"]))
+    ident = torch.nn.Identity()
+
+    # VarNet_RNN (recurrent_varnet.py:65-90): (b,2,h,w,t) image layout
+    rnn = types.SimpleNamespace(Softplus=torch.nn.Softplus(1.), lambda_reg=lam)
+    x_rnn = img.squeeze(2).permute(0, 4, 2, 3, 1)                                   # b,2,h,w,t (non-contiguous view)
+    x_np = np.transpose(d["img"][:, :, 0], (0, 4, 2, 3, 1))
+    assert rel(blocks.varnet_rnn_sens_expand(rnn, x_rnn, sens), O.sens_expand(d["img"], d["sens"])) <= TOL
+    assert rel(blocks.varnet_rnn_sens_reduce(rnn, k, sens),
+               np.transpose(O.sens_reduce(d["k"], d["sens"], keepdim=False), (0, 4, 2, 3, 1))) <= TOL
+    assert rel(blocks.varnet_rnn_data_consistency(rnn, x_rnn, ref, mask, sens),
+               O.varnet_rnn_data_consistency(x_np, d["ref"], d["mask"], d["sens"], v)) <= TOL
+
+    # xfyf transforms with identity regularisers == ifft1c(fft1c(x - mean)) + mean == x   (varnet.py:196-241, cinenet.py:174-219)
+    for fn, model in ((blocks.varnet_xfyf_transform, [ident, ident]), (blocks.cinenet_xfyf_transform, [ident, ident])):
+        for dyn in ("XF", "XT"):
+            blk = types.SimpleNamespace(dynamic_type=dyn, weight_sharing=False, model=model)
+            out = fn(blk, img.squeeze(2))
+            assert out.shape == (b, t, 1, h, w, 2)
+            assert rel(out, d["img"]) <= TOL
+    blk = types.SimpleNamespace(dynamic_type="XF", weight_sharing=True, model=ident)
+    assert rel(blocks.varnet_xfyf_transform(blk, img.squeeze(2)), d["img"]) <= TOL
+
+    # VarNetBlock.forward for every dynamic type with identity regularisers (varnet.py:244-282)
+    want = O.varnet_block(d["k"], d["ref"], d["mask"], d["sens"], v)
+    for dyn, model in (("2D", ident), ("3D", ident), ("XF", [ident, ident]), ("XT", [ident, ident])):
+        blk = types.SimpleNamespace(dynamic_type=dyn, weight_sharing=False, model=model, Softplus=torch.nn.Softplus(1.), lambda_reg=lam)
+        blk.xfyf_transform = types.MethodType(blocks.varnet_xfyf_transform, blk)
+        assert rel(blocks.varnet_block_forward(blk, k, ref, mask, sens), want) <= TOL, dyn
+
+    # SensitivityModel.forward, VarNet and XPDNet flavours, U-Net = identity (varnet.py:62-86, xpdnet.py:73-100)
+    mk = O.apply_mask(d["k"], d["mask"])
+    pre = O.sens_model_pre(mk, d["mask"])
+    sm = types.SimpleNamespace(norm_unet=ident, chans_to_batch_dim=lambda x: (x.view(b * c, 1, h, w, 2), b),
+                               batch_chans_to_chan_dim=lambda x, bb: x.view(bb, c, h, w, 2))
+    got = blocks.varnet_sens_model_forward(sm, cu(mk.astype(np.float32)), mask)
+    assert rel(got, O.divide_root_sum_of_squares(pre)[:, None]) <= 5e-5
+    xm = types.SimpleNamespace(unet_model=lambda x: torch.zeros_like(x), res_connection=True,
+                               chans_to_batch_dim=lambda x: (b, x.view(b * c, h, w, 2).permute(0, 3, 1, 2)),
+                               batch_chans_to_chan_dim=lambda x, bb: x.view(bb, c, 2, h, w).permute(0, 1, 3, 4, 2))
+    got = blocks.xpdnet_sens_model_forward(xm, cu(mk.astype(np.float32)), mask)
+    assert rel(got, O.divide_root_sum_of_squares(pre)[:, None]) <= 5e-5
+
+    # VarNet.forward / CineNet.forward drop-ins with identity cascades
+    class Casc(torch.nn.Module):
+        def forward(self, kk, rk, mm, ss):
+            return blocks.varnet_block_forward(types.SimpleNamespace(dynamic_type="2D", model=ident, Softplus=torch.nn.Softplus(1.),
+                                                                     lambda_reg=lam), kk, rk, mm, ss)
+    net = types.SimpleNamespace(sens_net=lambda kk, mm: sens, cascades=[Casc(), Casc()])
+    out = blocks.varnet_forward(net, cu(mk.astype(np.float32)), mask)
+    kk = mk
+    for _ in range(2):
+        kk = O.varnet_block(kk, mk, d["mask"], d["sens"], v)
+    assert rel(out, O.complex_abs(O.sens_reduce(kk, d["sens"], keepdim=False))) <= 2e-5
+    cine = types.SimpleNamespace(cascades=[lambda ip, ir, mm, ss: ip + ir])
+    out = blocks.cinenet_forward(cine, cu(mk.astype(np.float32)), mask, sens)
+    assert rel(out, O.complex_abs(2 * O.sens_reduce(mk, d["sens"], keepdim=False))) <= TOL
+
+
 # ------------------------------- golden fixtures ---------------------------- #
 GOLD = np.load(G.HERE / "golden_v1.npz")
 
