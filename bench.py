@@ -159,6 +159,10 @@ def run_ours(args, rank, world, local):
         raise SystemExit("bench.py: no CUDA device (the b200sense operators have no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if not _lib.LIB_PATH.exists():          # built artefacts normally travel with the tree
+        if rank == 0:
+            _lib.build()
+        bdist.barrier()
     lib = _lib.lib()
     nb, K, W = CFG["slices_per_gpu_step"], args.steps, args.warmup
     mk_np, mask_np = make_inputs(rank, nb)

@@ -4,7 +4,7 @@
 
 namespace b2s {
 static thread_local char g_err[512] = "";
-unsigned long long g_kernel_launches = 0;
+std::atomic<unsigned long long> g_kernel_launches{0};
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -16,7 +16,5 @@ void set_error(const char* fmt, ...) {
 extern "C" int b2s_version(void) { return 100; }
 extern "C" const char* b2s_last_error(void) { return b2s::g_err; }
 extern "C" unsigned long long b2s_launch_count(int reset) {
-  const unsigned long long n = b2s::g_kernel_launches;
-  if (reset) b2s::g_kernel_launches = 0;
-  return n;
+  return reset ? b2s::g_kernel_launches.exchange(0) : b2s::g_kernel_launches.load();
 }

@@ -1,6 +1,7 @@
 // Shared host-side helpers of the C-ABI translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -12,10 +13,10 @@ void set_error(const char* fmt, ...);          // defined in b2s_abi.cu (thread-
 
 inline int fail(int code, const char* what) { set_error("%s", what); return code; }
 
-extern unsigned long long g_kernel_launches;   // b2s_abi.cu; kernels launched through this library
+extern std::atomic<unsigned long long> g_kernel_launches;   // b2s_abi.cu; kernels launched through this library
 
 inline int check_launch(const char* what, int n_kernels = 1) {
-  g_kernel_launches += (unsigned long long)n_kernels;
+  g_kernel_launches.fetch_add((unsigned long long)n_kernels, std::memory_order_relaxed);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return B2S_ECUDA; }
   return B2S_OK;

@@ -26,14 +26,14 @@ int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, 
   auto kern = fft2_half_kernel<P, Pro, Epi, CARRY>;
   int dev = 0, sms = 0;
   B2S_CUDA(cudaGetDevice(&dev));
-  static int sm_count[64] = {0};             // immutable per-device facts
-  static bool configured[64] = {false};      // per instantiation and device
+  static std::atomic<int> sm_count[64];       // immutable per-device facts (zero-initialised statics)
+  static std::atomic<bool> configured[64];    // per instantiation and device; setting the attribute twice is harmless
   if (dev < 0 || dev >= 64) return fail(B2S_EUNSUPPORTED, "device index >= 64");
-  if (!sm_count[dev]) B2S_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-  sms = sm_count[dev];
-  if (!configured[dev]) {
+  if (!sm_count[dev].load()) { int n = 0; B2S_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); sm_count[dev].store(n); }
+  sms = sm_count[dev].load();
+  if (!configured[dev].load()) {
     B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<P>::SMEM_BYTES));
-    configured[dev] = true;
+    configured[dev].store(true);
   }
   const int n_items = (int)(P::FOLD * n_images);
   const int slots = sms * P::CTAS;
@@ -52,15 +52,15 @@ int launch_pair(const Pro& pro, const Epi& epi, float scale, int64_t n_images, c
   auto kern = fft2_pair_kernel<P, Pro, Epi, CARRY>;
   int dev = 0;
   B2S_CUDA(cudaGetDevice(&dev));
-  static int sm_count[64] = {0};
-  static bool configured[64] = {false};
+  static std::atomic<int> sm_count[64];
+  static std::atomic<bool> configured[64];
   if (dev < 0 || dev >= 64) return fail(B2S_EUNSUPPORTED, "device index >= 64");
-  if (!sm_count[dev]) B2S_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-  if (!configured[dev]) {
+  if (!sm_count[dev].load()) { int n = 0; B2S_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); sm_count[dev].store(n); }
+  if (!configured[dev].load()) {
     B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<P>::SMEM_BYTES));
-    configured[dev] = true;
+    configured[dev].store(true);
   }
-  const long long max_pairs = sm_count[dev] / 2;
+  const long long max_pairs = sm_count[dev].load() / 2;
   const unsigned pairs = (unsigned)(n_images < max_pairs ? n_images : max_pairs);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(P::NT); cfg.dynamicSmemBytes = Derived<P>::SMEM_BYTES; cfg.stream = st;

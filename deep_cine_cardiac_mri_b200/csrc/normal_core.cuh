@@ -27,7 +27,8 @@ template <int H_, int XC_> struct NormalPlan {
   static constexpr int NT = 8 * XC_;
   static constexpr int E_ELEMS = H_ * XC_;           // exchange buffer [g][m][x]
   static constexpr int X_OFF = E_ELEMS;              // this CTA's columns of x_t, [row][x] (read by every coil)
-  static constexpr int TW_OFF = X_OFF + H_ * XC_;    // w_H^n, n in [0,H)
+  static constexpr int L_OFF = X_OFF + H_ * XC_;     // landing buffer of the NEXT coil's S values (cp.async, thread-private slots)
+  static constexpr int TW_OFF = L_OFF + H_ * XC_;    // w_H^n, n in [0,H)
   static constexpr int SMEM_ELEMS = TW_OFF + H_;
   static constexpr int SMEM_BYTES = SMEM_ELEMS * 8 + H_;   // + mask row (uint8)
   static constexpr int TASKS2 = G * XC_;
@@ -54,18 +55,42 @@ B2S_HD void normal_stage_x(const NormalArgs& a, cfloat* smem, long long bt, int 
   for (int i = 0; i < G; ++i) smem[P::X_OFF + (m + 8 * i) * XC + xl] = xp[(long long)(m + 8 * i) * a.W];
 }
 
+// asynchronous copy of one 8-byte element global -> shared (cp.async); a plain copy on the host
+B2S_HD void async_copy8(cfloat* dst_smem, const cfloat* src) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+#else
+  *dst_smem = *src;
+#endif
+}
+B2S_HD void async_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// this thread's 25 values of S_c into its own slots of the landing buffer (read back only by this thread)
+template <class P>
+B2S_HD void normal_prefetch_s(const NormalArgs& a, cfloat* smem, long long bt, int c, int x0, int tid) {
+  constexpr int G = P::G, XC = P::XC;
+  const int m = tid / XC, xl = tid - m * XC;
+  const long long b = bt / a.T;
+  const cfloat* sp = a.sens + (b * a.C + c) * (long long)P::H * a.W + x0 + xl;
+#pragma unroll
+  for (int i = 0; i < G; ++i) async_copy8(smem + P::L_OFF + (m + 8 * i) * XC + xl, sp + (long long)(m + 8 * i) * a.W);
+}
+
 // step 1: p = S_c x, radix-G over this thread's rows, twiddle, store E[g][m][xl]; S_c values stay in sv
 template <class P>
 B2S_HD void normal_step1(const NormalArgs& a, cfloat* smem, long long bt, int c, int x0, int tid, cfloat (&sv)[P::G]) {
   constexpr int G = P::G, XC = P::XC;
-  const int m = tid / XC, xl = tid - m * XC, x = x0 + xl;
-  const long long b = bt / a.T;
-  const long long hw = (long long)P::H * a.W;
-  const cfloat* sp = a.sens + (b * a.C + c) * hw + x;
+  const int m = tid / XC, xl = tid - m * XC;
   float re[G], im[G];
   const float sg = (m & 1) ? -1.f : 1.f;
+  async_wait_all();                                   // S_c landed (issued one coil ago)
 #pragma unroll
-  for (int i = 0; i < G; ++i) sv[i] = sp[(long long)(m + 8 * i) * a.W];
+  for (int i = 0; i < G; ++i) sv[i] = smem[P::L_OFF + (m + 8 * i) * XC + xl];
+  if (c + 1 < a.C) normal_prefetch_s<P>(a, smem, bt, c + 1, x0, tid);   // S_{c+1} streams in behind this coil's math
 #pragma unroll
   for (int i = 0; i < G; ++i) {
     const cfloat xv = smem[P::X_OFF + (m + 8 * i) * XC + xl];
@@ -148,7 +173,7 @@ B2S_HD void normal_finish(const NormalArgs& a, const cfloat* smem, long long bt,
 
 #if defined(__CUDACC__)
 template <class P>
-__global__ void __launch_bounds__(P::NT, 3) normal_op_kernel(const NormalArgs a) {
+__global__ void __launch_bounds__(P::NT, 2) normal_op_kernel(const NormalArgs a) {
   extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
   cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);
   uint8_t* mrow = reinterpret_cast<uint8_t*>(smem + P::SMEM_ELEMS);
@@ -158,6 +183,7 @@ __global__ void __launch_bounds__(P::NT, 3) normal_op_kernel(const NormalArgs a)
   const int x0 = (blockIdx.x % chunks) * P::XC;
   for (int n = tid; n < P::H; n += P::NT) { smem[P::TW_OFF + n] = twiddle(n, P::H); mrow[n] = a.mask[bt * P::H + n]; }
   normal_stage_x<P>(a, smem, bt, x0, tid);            // each thread only ever reads back its own rows
+  normal_prefetch_s<P>(a, smem, bt, 0, x0, tid);
   float accr[P::G], acci[P::G];
   cfloat sv[P::G];
 #pragma unroll
@@ -190,7 +216,7 @@ void normal_op_emulate(const NormalArgs& a, long long n_bt) {
     const int x0 = (int)(blk % chunks) * P::XC;
     for (int n = 0; n < P::H; ++n) { smem[P::TW_OFF + n] = twiddle(n, P::H); mrow[n] = a.mask[bt * P::H + n]; }
     for (int tid = 0; tid < P::NT; ++tid) for (int k = 0; k < P::G; ++k) { accr[tid][k] = 0.f; acci[tid][k] = 0.f; }
-    for (int tid = 0; tid < P::NT; ++tid) normal_stage_x<P>(a, smem, bt, x0, tid);
+    for (int tid = 0; tid < P::NT; ++tid) { normal_stage_x<P>(a, smem, bt, x0, tid); normal_prefetch_s<P>(a, smem, bt, 0, x0, tid); }
     for (int c = 0; c < a.C; ++c) {
       for (int tid = 0; tid < P::NT; ++tid) normal_step1<P>(a, smem, bt, c, x0, tid, sv[tid]);
       for (int tid = 0; tid < P::NT; ++tid)

@@ -53,8 +53,38 @@ template <> __device__ __forceinline__ cvec<2> ldv<2>(const cfloat* p) {
   const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
   cvec<2> r; r.v[0].x = t.x; r.v[0].y = t.y; r.v[1].x = t.z; r.v[1].y = t.w; return r;
 }
+// L2 cache-policy hints: operands that are re-read many times per launch (sens maps: once per frame, the
+// coil-combined image: once per coil) are kept with evict_last, the k-space streams (read or written once)
+// are marked evict_first so that they do not push those operands out of L2.
+__device__ __forceinline__ unsigned long long l2_keep() { unsigned long long p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ unsigned long long l2_stream() { unsigned long long p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+template <int NC> __device__ __forceinline__ cvec<NC> ldv_pol(const cfloat* p, unsigned long long pol);
+template <> __device__ __forceinline__ cvec<1> ldv_pol<1>(const cfloat* p, unsigned long long pol) {
+  cvec<1> r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(r.v[0].x), "=f"(r.v[0].y) : "l"(p), "l"(pol));
+  return r;
+}
+template <> __device__ __forceinline__ cvec<2> ldv_pol<2>(const cfloat* p, unsigned long long pol) {
+  cvec<2> r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(r.v[0].x), "=f"(r.v[0].y), "=f"(r.v[1].x), "=f"(r.v[1].y) : "l"(p), "l"(pol));
+  return r;
+}
+template <int NC> __device__ __forceinline__ void stv_pol(cfloat* p, const cvec<NC>& v, unsigned long long pol);
+template <> __device__ __forceinline__ void stv_pol<1>(cfloat* p, const cvec<1>& v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.v[0].x), "f"(v.v[0].y), "l"(pol) : "memory");
+}
+template <> __device__ __forceinline__ void stv_pol<2>(cfloat* p, const cvec<2>& v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.v[0].x), "f"(v.v[0].y), "f"(v.v[1].x), "f"(v.v[1].y), "l"(pol) : "memory");
+}
+template <int NC> __device__ __forceinline__ cvec<NC> ldv_keep(const cfloat* p) { return ldv_pol<NC>(p, l2_keep()); }
+template <int NC> __device__ __forceinline__ cvec<NC> ldv_stream(const cfloat* p) { return ldv_pol<NC>(p, l2_stream()); }
+template <int NC> __device__ __forceinline__ void stv_stream(cfloat* p, const cvec<NC>& v) { stv_pol<NC>(p, v, l2_stream()); }
 #else
 template <int NC> inline cvec<NC> ldv(const cfloat* p) { return *reinterpret_cast<const cvec<NC>*>(p); }
+template <int NC> inline cvec<NC> ldv_keep(const cfloat* p) { return ldv<NC>(p); }
+template <int NC> inline cvec<NC> ldv_stream(const cfloat* p) { return ldv<NC>(p); }
+template <int NC> inline void stv_stream(cfloat* p, const cvec<NC>& v) { *reinterpret_cast<cvec<NC>*>(p) = v; }
 #endif
 template <int NC> B2S_HD void stv(cfloat* p, const cvec<NC>& v) { *reinterpret_cast<cvec<NC>*>(p) = v; }
 
@@ -107,7 +137,7 @@ template <int H, int W> struct ProExpand {
   template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int, int off, Unit<NC>& u) const {
     const cfloat* pa = c.a + off; const cfloat* ps = c.s + off;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { u.a[j] = ldv<NC>(pa + j * RS); u.s[j] = ldv<NC>(ps + j * RS); }
+    for (int j = 0; j < 8; ++j) { u.a[j] = ldv_keep<NC>(pa + j * RS); u.s[j] = ldv_keep<NC>(ps + j * RS); }
   }
   template <int NC> B2S_HD void value(const Unit<NC>& u, int j, float* re, float* im) const {
 #pragma unroll
@@ -208,7 +238,7 @@ template <int H, int W, int MODE> struct EpiKspace {
     if (MODE >= 2) {
 #pragma unroll
       for (int k = 0; k < G; ++k)                          // DC needs ref on sampled rows only
-        if (MODE == 3 || ((pre.mbits >> k) & 1u)) pre.r[k] = ldv<NC>(t.r + 8 * k * W);
+        if (MODE == 3 || ((pre.mbits >> k) & 1u)) pre.r[k] = ldv_stream<NC>(t.r + 8 * k * W);
     }
   }
   template <int G, int NC> B2S_HD void store(const Ptr& t, int k, const float* re_in, const float* im_in, const Pre<G, NC>& pre) const {
@@ -233,7 +263,7 @@ template <int H, int W, int MODE> struct EpiKspace {
       for (int n = 0; n < NC; ++n)
         o.v[n] = mk ? make_c(re_in[n] - r.v[n].x, im_in[n] - r.v[n].y) : make_c(0.f - r.v[n].x, 0.f - r.v[n].y);
     }
-    stv<NC>(t.p + 8 * k * W, o);
+    stv_stream<NC>(t.p + 8 * k * W, o);
   }
   // the reference k-space this item will blend with (whole image: the sibling half needs the rest)
   B2S_HD void l2_prefetch(long long image, int q, int tid) const {
@@ -257,7 +287,7 @@ template <int H, int W> struct EpiReduce {
   template <int G, int NC> struct Pre { cvec<NC> s[G]; };
   template <int G, int NC> B2S_HD void prefetch(const Ptr& t, Pre<G, NC>& pre) const {
 #pragma unroll
-    for (int k = 0; k < G; ++k) pre.s[k] = ldv<NC>(t.m + 8 * k * W);
+    for (int k = 0; k < G; ++k) pre.s[k] = ldv_keep<NC>(t.m + 8 * k * W);
   }
   template <int G, int NC> B2S_HD void store(const Ptr& t, int k, const float* re, const float* im, const Pre<G, NC>& pre) const {
     const cvec<NC> s = pre.s[k];

@@ -25,3 +25,15 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """Build libb2sense.so if the tree arrived without it (nvcc cross-compiles without a GPU)."""
+    try:
+        from deep_cine_cardiac_mri_b200 import _lib
+        if not _lib.LIB_PATH.exists():
+            _lib.build()
+    except Exception as e:                       # the tests that need it will fail loudly on their own
+        print("could not build libb2sense.so:", e)
+    yield
