@@ -138,6 +138,24 @@ int plan_reduce(const float* kspace, const float* mult, float* out, const uint8_
 #undef B2S_RUN
 }
 
+// Deterministic variant of plan_reduce: weighted inverse transform of every coil image into `y` (no float
+// atomics); the caller then sums the coils in a fixed order (launch_coil_reduce).
+template <class P>
+int plan_ifft_weighted(const float* kspace, float* y, const uint8_t* mask, const float* v, int weight_mode,
+                       int c, int64_t n, float scale, cudaStream_t st) {
+  constexpr int H = P::H, W = P::W;
+  const long long hw = (long long)H * W;
+  const float s = scale * centre_sign<P>();
+  EpiPlain<H, W, true> epi{(cfloat*)y, hw};
+#define B2S_RUN(M)                                                      \
+  {                                                                     \
+    ProKspace<H, W, M> pro{(const cfloat*)kspace, mask, v, c, hw};      \
+    return launch_fused<P>(pro, epi, s, n, st);                         \
+  }
+  switch (weight_mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) default: B2S_RUN(2) }
+#undef B2S_RUN
+}
+
 static inline int plan_id(int h, int w) { return (h == 200 && w == 200) ? 1 : (h == 256 && w == 256) ? 2 : 0; }
 
 extern "C" int b2s_has_fused_plan(int h, int w) { return plan_id(h, w) ? 1 : 0; }
@@ -192,6 +210,8 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
 extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* out, const uint8_t* mask,
                                const float* v, int weight_mode, int over_frames, int b, int t, int c,
                                int h, int w, int norm, void* scratch, size_t scratch_bytes, void* stream) {
+  const int deterministic = (weight_mode & B2S_REDUCE_DETERMINISTIC) ? 1 : 0;
+  weight_mode &= ~B2S_REDUCE_DETERMINISTIC;
   if (b < 0 || t < 0 || c < 0 || bad_norm(norm) || weight_mode < 0 || weight_mode > 2)
     return fail(B2S_EINVAL, "b2s_sens_reduce: bad argument");
   if ((over_frames ? (int64_t)b * c : (int64_t)b * t) == 0) return B2S_OK;
@@ -203,6 +223,15 @@ extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* ou
   const int64_t hw = (int64_t)h * w;
   const float scale = norm_scale(h, w, 1, norm);
   const int64_t out_images = over_frames ? (int64_t)b * c : (int64_t)b * t;
+  if (plan_id(h, w) && deterministic && n > 0) {
+    const size_t need = (size_t)n * hw * 2 * sizeof(float);
+    if (!scratch || scratch_bytes < need) return fail(B2S_EINVAL, "b2s_sens_reduce: deterministic mode needs b*t*c*h*w*8 scratch bytes");
+    float* y = (float*)scratch;
+    const int rc = plan_id(h, w) == 2 ? plan_ifft_weighted<P256>(kspace, y, mask, v, weight_mode, c, n, scale, st)
+                                      : plan_ifft_weighted<P200H>(kspace, y, mask, v, weight_mode, c, n, scale, st);
+    if (rc) return rc;
+    return launch_coil_reduce(y, mult, out, over_frames, b, t, c, hw, st);
+  }
   if (plan_id(h, w)) {
     B2S_CUDA(cudaMemsetAsync(out, 0, (size_t)out_images * hw * 2 * sizeof(float), st));
     if (n == 0) return B2S_OK;

@@ -148,9 +148,9 @@ __global__ void dc_blend_bwd_kernel(const V* g, const V* outv, const V* ref, con
       for (int e = 0; e < VecOps<V>::N; ++e) acc += gg[e] * (r[e] - o[e]) * inv1;
     }
   }
-  if (gv) {
+  if (gv) {                                   // ordered two-stage sum: partials here, dot_final_kernel after
     acc = block_sum(acc);
-    if (threadIdx.x == 0) atomicAdd(gv, acc);
+    if (threadIdx.x == 0) gv[B2S_DC_BWD_GV_FLOATS - 1024 + blockIdx.x] = acc;
   }
 }
 
@@ -437,13 +437,17 @@ extern "C" int b2s_dc_blend_bwd(const float* g, const float* out, const float* r
   if (n == 0) return B2S_OK;
   if (!g || !mask || !v || (gv && (!out || !ref))) return fail(B2S_EINVAL, "b2s_dc_blend_bwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
+  const long long nv = (w % 2 == 0) ? n / 2 : n;
+  const unsigned grid = grid_for(nv, NT, gv ? 1024 : 148LL * 16);
   if (w % 2 == 0)
-    dc_blend_bwd_kernel<float4><<<grid_for(n / 2), NT, 0, st>>>((const float4*)g, (const float4*)out, (const float4*)ref, mask, v,
-                                                                (float4*)gk, (float4*)gref, gv, c, h, w / 2, n / 2);
+    dc_blend_bwd_kernel<float4><<<grid, NT, 0, st>>>((const float4*)g, (const float4*)out, (const float4*)ref, mask, v,
+                                                     (float4*)gk, (float4*)gref, gv, c, h, w / 2, nv);
   else
-    dc_blend_bwd_kernel<cfloat><<<grid_for(n), NT, 0, st>>>((const cfloat*)g, (const cfloat*)out, (const cfloat*)ref, mask, v,
-                                                            (cfloat*)gk, (cfloat*)gref, gv, c, h, w, n);
-  return check_launch("dc_blend_bwd_kernel");
+    dc_blend_bwd_kernel<cfloat><<<grid, NT, 0, st>>>((const cfloat*)g, (const cfloat*)out, (const cfloat*)ref, mask, v,
+                                                     (cfloat*)gk, (cfloat*)gref, gv, c, h, w, nv);
+  if (!gv) return check_launch("dc_blend_bwd_kernel");
+  dot_final_kernel<<<1, NT, 0, st>>>(gv + B2S_DC_BWD_GV_FLOATS - 1024, gv, (int)grid);
+  return check_launch("dc_blend_bwd kernels", 2);
 }
 
 extern "C" int b2s_complex_mul(const float* a, const float* b, float* out, int ndim, const int64_t* shape,

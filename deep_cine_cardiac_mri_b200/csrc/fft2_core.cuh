@@ -27,6 +27,14 @@
 #include <stdint.h>
 #include "codelets.cuh"
 
+// CTA barrier inside host/device phase code: the host emulation runs one phase for all thread ids in
+// turn, so there it is a no-op.
+#if defined(__CUDA_ARCH__)
+#define B2S_CTA_SYNC() __syncthreads()
+#else
+#define B2S_CTA_SYNC() ((void)0)
+#endif
+
 namespace b2s {
 
 struct alignas(8) cfloat { float x, y; };
@@ -163,6 +171,7 @@ template <class P, class Pro> struct PhaseA {
   }
 
   // consume the queue for one work item (half q), refilling it from this item and then the next
+  template <bool SYNC_FIRST = false>
   static B2S_HD void run(const Pro& pro, const typename Pro::Ctx& ctx, const typename Pro::Ctx& next, bool has_next,
                          cfloat* smem, int q, int tid, Queue& qu) {
     const float h = 0.70710678118654752440f;
@@ -220,6 +229,9 @@ template <class P, class Pro> struct PhaseA {
       if (s + QD < STEPS) issue(pro, ctx, tid, s + QD, qu.u[slot]);
       else if (has_next) issue(pro, next, tid, s + QD - STEPS, qu.u[slot]);
       // ---- last column group of the task: row twiddles, radix-R over i, column twiddles, store
+      if (SYNC_FIRST && u == R - 1) {          // first write into B of this item: every warp must have left
+        if (kp == 0) B2S_CTA_SYNC();           // the previous item's Phase C (its ragged last round overlaps
+      }                                        // the loads issued above instead of idling 7 of 8 warps)
       if (i == R - 1 && valid) {
         cfloat th[NK];
 #pragma unroll

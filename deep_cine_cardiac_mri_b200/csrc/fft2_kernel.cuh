@@ -54,10 +54,12 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
     const int q = item % P::FOLD;
     const int next = item + (int)gridDim.x;
     const bool has_next = next < n_items;
-    epi.stage_mask(image, mrow, tid, P::NT);               // visible to Phase C through the barriers below
     if (!CARRY) PA::prefill(pro, pro.ctx(image), tid, queue);
-    PA::run(pro, pro.ctx(image), pro.ctx(has_next ? (next / P::FOLD) : image), CARRY && has_next, smem, q, tid, queue);
+    // run<true>: the barrier that protects B (and the mask rows) from the previous item's Phase C sits
+    // inside, just before the first write into B, so the first loads of this item are already in flight
+    PA::template run<true>(pro, pro.ctx(image), pro.ctx(has_next ? (next / P::FOLD) : image), CARRY && has_next, smem, q, tid, queue);
     __syncthreads();
+    epi.stage_mask(image, mrow, tid, P::NT);               // visible to Phase C through the barriers below
     B2S_TICK(0);
     // warm L2 with the rest of the next item while this SM is busy with register codelets (Phases B, C)
     if (has_next && (next % P::FOLD) == 0) pro.l2_prefetch(next / P::FOLD, tid);
@@ -79,8 +81,7 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
       const typename Epi::Ctx ectx = epi.ctx(image, mrow);
       for (int task = tid; task < D::TASKS_C; task += P::NT) phase_c<P>(epi, ectx, smem, q, task, scale);
     }
-    __syncthreads();                                       // B is rewritten by the next item's Phase A
-    B2S_TICK(3);
+    B2S_TICK(3);                                           // no barrier here: see run<true>
   }
 }
 

@@ -18,6 +18,8 @@ NORM = {None: 0, "backward": 0, "ortho": 1, "forward": 2}
 _ADJ_NORM = {0: 2, 1: 1, 2: 0}          # adjoint of a transform with norm n is the inverse with this norm
 EXPAND_PLAIN, EXPAND_MASK, EXPAND_DC, EXPAND_RESIDUAL = 0, 1, 2, 3
 REDUCE_PLAIN, REDUCE_MASK, REDUCE_DCGRAD = 0, 1, 2
+REDUCE_DETERMINISTIC = 0x10       # OR-ed into the weight mode: ordered coil sum, no float atomics
+DC_BWD_GV_FLOATS = 1032           # include/b200sense.h: B2S_DC_BWD_GV_FLOATS
 
 
 # --------------------------------------------------------------------------- #
@@ -76,8 +78,23 @@ def _vdev(v, device) -> torch.Tensor:
 _scratch = {}
 
 
-def _scratch_for(b, t, c, h, w, device):
-    n = _lib.lib().b2s_scratch_bytes(b, t, c, h, w)
+_force_deterministic = False
+
+
+def set_deterministic(flag: bool) -> None:
+    """Force the ordered (atomics-free) coil sum in `sens_reduce` regardless of torch's global switch."""
+    global _force_deterministic
+    _force_deterministic = bool(flag)
+
+
+def deterministic() -> bool:
+    """True when results must be run-to-run bit-identical: `torch.use_deterministic_algorithms(True)` (what
+    the reference's `Trainer(deterministic=True)` sets, train_test_varnet.py:292) or `set_deterministic(True)`."""
+    return _force_deterministic or torch.are_deterministic_algorithms_enabled()
+
+
+def _scratch_for(b, t, c, h, w, device, full=False):
+    n = b * t * c * h * w * 8 if full else _lib.lib().b2s_scratch_bytes(b, t, c, h, w)
     if n == 0:
         return None, 0
     key = (device.index, "s")
@@ -126,7 +143,10 @@ def raw_sens_reduce(kspace, mult, wmode=REDUCE_PLAIN, over_frames=False, mask_u8
     b, t, c, h, w, _ = kspace.shape
     shape = (b, c, h, w, 2) if over_frames else (b, t, h, w, 2)
     out = torch.empty(shape, dtype=torch.float32, device=kspace.device)
-    sc, nsc = _scratch_for(b, t, c, h, w, kspace.device)
+    det = deterministic()
+    if det:
+        wmode |= REDUCE_DETERMINISTIC
+    sc, nsc = _scratch_for(b, t, c, h, w, kspace.device, full=det)
     _lib.check(_lib.lib().b2s_sens_reduce(_p(kspace), _p(mult), _p(out), _p(mask_u8), _p(v), wmode,
                                           int(over_frames), b, t, c, h, w, norm, _p(sc), nsc, _stream()),
                "sens_reduce")
@@ -146,10 +166,10 @@ def raw_dc_blend_bwd(g, out, ref, mask_u8, v, want_gk, want_gref, want_gv):
     b, t, c, h, w, _ = g.shape
     gk = torch.empty_like(g) if want_gk else None
     gref = torch.empty_like(g) if want_gref else None
-    gv = torch.zeros(1, dtype=torch.float32, device=g.device) if want_gv else None
+    gv = torch.empty(DC_BWD_GV_FLOATS, dtype=torch.float32, device=g.device) if want_gv else None
     _lib.check(_lib.lib().b2s_dc_blend_bwd(_p(g), _p(out), _p(ref), _p(mask_u8), _p(v), _p(gk), _p(gref), _p(gv),
                                            b * t, c, h, w, _stream()), "dc_blend_bwd")
-    return gk, gref, gv
+    return gk, gref, (gv[:1] if want_gv else None)
 
 
 def raw_normal_op(x, sens, mask_u8, v):

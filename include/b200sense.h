@@ -47,6 +47,10 @@ extern "C" {
 #define B2S_REDUCE_PLAIN 0    /* A^H k                           varnet.py:187-194          */
 #define B2S_REDUCE_MASK 1     /* A^H (k*m)                       xpdnet.py:161-167          */
 #define B2S_REDUCE_DCGRAD 2   /* A^H (k*(1 - v/(1+v) m))         backward of B2S_EXPAND_DC  */
+/* OR into weight_mode: sum the coils in a fixed order instead of with float atomics (run-to-run
+ * bit-identical results, for the reference's Trainer(deterministic=True), train_test_varnet.py:292).
+ * Costs one extra K-sized round trip; needs b*t*c*h*w*8 bytes of scratch for every shape. */
+#define B2S_REDUCE_DETERMINISTIC 0x10
 
 int b2s_version(void);
 const char* b2s_last_error(void);
@@ -88,7 +92,9 @@ int b2s_sens_reduce(const float* kspace, const float* mult, float* out, const ui
 int b2s_dc_blend(const float* kspace, const float* ref, const uint8_t* mask, const float* v,
                  float* out, int64_t n_bt, int c, int h, int w, void* stream);
 /* Its backward: gk = g(1 - eta m), gref = g eta m (either may be NULL),
- * gv[0] += sum g m (ref - out)/(1+v); gv must be zeroed by the caller. */
+ * gv[0] = sum g m (ref - out)/(1+v) (ordered two-stage sum, no float atomics); gv (may be NULL)
+ * points to B2S_DC_BWD_GV_FLOATS floats: element 0 is the result, the rest is workspace. */
+#define B2S_DC_BWD_GV_FLOATS 1032
 int b2s_dc_blend_bwd(const float* g, const float* out, const float* ref, const uint8_t* mask,
                      const float* v, float* gk, float* gref, float* gv, int64_t n_bt, int c, int h,
                      int w, void* stream);

@@ -370,3 +370,21 @@ def test_bench_reference_arm_json():
     assert j["impl"] == "reference" and j["metric"] == "cine_slices_per_sec" and j["unit"] == "slices/s"
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["value"] > 0
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["higher_is_better"] is True
+
+
+def test_dispatcher_custom_ops_registered_with_fake_kernels():
+    """torch.ops.b200sense.* exist, propagate shapes under FakeTensorMode (no GPU, no library call) and
+    refuse real CPU tensors loudly."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from deep_cine_cardiac_mri_b200 import torch_ops  # noqa: F401
+    T = torch.ops.b200sense
+    with FakeTensorMode():
+        x, s = torch.empty(2, 3, 20, 20, 2), torch.empty(2, 4, 20, 20, 2)
+        m, v = torch.empty(2, 3, 20, dtype=torch.uint8), torch.empty(1)
+        k = T.sens_expand(x, s, None, m, v, 1, 1)
+        assert tuple(k.shape) == (2, 3, 4, 20, 20, 2)
+        assert tuple(T.sens_reduce(k, s, m, 1, 1).shape) == (2, 3, 20, 20, 2)
+        assert tuple(T.fft2c(x, True, 1).shape) == tuple(x.shape)
+        assert tuple(T.normal_op(x, s, m, v).shape) == tuple(x.shape)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        T.fft2c(torch.zeros(1, 4, 4, 2), False, 1)

@@ -518,3 +518,88 @@ def test_dc_step_host_entry():
     torch.cuda.synchronize()
     want = O.varnet_block(f64(cs["k"]), f64(cs["ref"]), cs["mask"], f64(cs["sens"]), v)
     assert rel(out, want) <= TOL
+
+
+def test_dispatcher_custom_ops_match_autograd_functions(ops):
+    """torch.ops.b200sense.* (torch.library custom ops with fake + autograd registrations) give the same
+    values and gradients as the autograd.Function tier, and pass torch.library.opcheck."""
+    from deep_cine_cardiac_mri_b200 import torch_ops  # noqa: F401  (registers the ops)
+    T = torch.ops.b200sense
+    b, t, c, h, w = 1, 2, 3, 200, 200
+    cs = G.sense_case(91, b, t, c, h, w)
+    m8 = ops._mask_u8(cu(cs["mask"]), b, t, h)
+
+    def leaves():
+        sens5 = cu(cs["sens"]).reshape(b, c, h, w, 2)             # the ABI layout (no singleton frame dim)
+        return [cu(cs["img"]).requires_grad_(True), sens5.requires_grad_(True), cu(cs["k"]).requires_grad_(True),
+                cu(cs["ref"]).requires_grad_(True), torch.tensor([0.3], device="cuda", requires_grad=True)]
+
+    def run(dispatcher):
+        img, sens, k, ref, lam = ls = leaves()
+        v = torch.nn.functional.softplus(lam)
+        if dispatcher:
+            x1 = T.sens_reduce(k, sens, None, ops.REDUCE_PLAIN, 1)
+            out = T.sens_expand(x1 + img[:, :, 0], sens, ref, m8, v, ops.EXPAND_DC, 1)
+            out2 = T.sens_reduce(out, sens, m8, ops.REDUCE_MASK, 1)
+            out3 = T.normal_op(out2, sens.detach(), m8, v) + T.fft2c(out2, False, 1)
+        else:
+            x1 = ops.sens_reduce(k, sens)
+            out = ops.sens_expand(x1 + img[:, :, 0], sens, ops.EXPAND_DC, ref=ref, mask=m8, v=v)
+            out2 = ops.sens_reduce(out, sens, mask=m8)
+            out3 = ops.normal_op(out2, sens.detach(), m8, v) + ops.fft2c(out2)
+        wgt = torch.linspace(0.5, 1.5, out3.numel(), device="cuda").view_as(out3)
+        loss = (out3 * wgt).sum() + (out * out).sum() * 0.1
+        loss.backward()
+        return [out3.detach()] + [l.grad for l in ls]
+
+    a, r = run(True), run(False)
+    for ga, gr, name in zip(a, r, ("out", "img", "sens", "k", "ref", "lam")):
+        assert ga is not None and gr is not None, name
+        assert float((ga - gr).abs().max() / gr.abs().max()) <= 2e-6, name   # atomics order only
+
+    x = cu(G.rng_normal(3, (2, 20, 12, 2))).requires_grad_(True)
+    torch.library.opcheck(T.fft2c.default, (x, False, 1), test_utils=("test_schema", "test_faketensor"))
+    img = cu(cs["img"])[:, :, 0]
+    torch.library.opcheck(T.sens_expand.default, (img, cu(cs["sens"]).reshape(b, c, h, w, 2), None, m8, None, ops.EXPAND_MASK, 1),
+                          test_utils=("test_schema", "test_faketensor"))
+
+
+@pytest.mark.parametrize("hw", [(200, 200), (256, 256), (18, 14)])
+def test_deterministic_mode_is_bit_reproducible(ops, hw):
+    """`torch.use_deterministic_algorithms(True)` (the reference's Trainer(deterministic=True),
+    train_test_varnet.py:292) switches sens_reduce to the ordered coil sum: same values within TOL,
+    bit-identical from run to run, forward and backward (incl. the eta gradient)."""
+    h, w = hw
+    b, t, c = 2, 3, 4
+    cs = G.sense_case(17, b, t, c, h, w)
+    k, sens, ref, mask = cu(cs["k"]), cu(cs["sens"]), cu(cs["ref"]), cu(cs["mask"])
+    want = O.sens_reduce(f64(cs["k"]), f64(cs["sens"]))[:, :, 0]
+
+    def step():
+        kk = k.clone().requires_grad_(True)
+        ss = sens.clone().requires_grad_(True)
+        lam = torch.tensor([0.2], device="cuda", requires_grad=True)
+        x = ops.sens_reduce(kk, ss)
+        out = ops.sens_expand(x, ss, ops.EXPAND_DC, ref=ref, mask=mask, v=torch.nn.functional.softplus(lam))
+        y = ops.sens_reduce(out, ss, mask=mask)
+        (y * y).sum().backward()
+        return x.detach(), y.detach(), kk.grad, ss.grad, lam.grad
+
+    free = step()
+    assert rel(free[0], want) <= TOL
+    torch.use_deterministic_algorithms(True)
+    try:
+        assert ops.deterministic()
+        a, bb = step(), step()
+    finally:
+        torch.use_deterministic_algorithms(False)
+    assert rel(a[0], want) <= TOL
+    for u, v_, f in zip(a, bb, free):
+        assert torch.equal(u, v_)
+        assert float((u - f).abs().max() / f.abs().max()) <= 2e-5
+    ops.set_deterministic(True)
+    try:
+        c3 = step()
+    finally:
+        ops.set_deterministic(False)
+    assert all(torch.equal(u, v_) for u, v_ in zip(a, c3))

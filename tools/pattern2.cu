@@ -4,6 +4,9 @@
 // MODE 0: kernel pattern float2 (x0 = task%40)      1: float4 pairs (xp = task%20)
 //      2: float2, 32-column groups (aligned 256 B)   3: flat streaming float4      4: flat streaming float2
 //      5: kernel pattern float2 but rows padded to 1664 B (13 lines)
+#ifndef LOADFN
+#define LOADFN __ldcg
+#endif
 template <int MODE> __global__ void __launch_bounds__(256, 1) pat(const float2* __restrict__ in, int n_items, float* out) {
   extern __shared__ float2 sm[];
   float acc = 0.f;
@@ -20,7 +23,7 @@ template <int MODE> __global__ void __launch_bounds__(256, 1) pat(const float2* 
 #pragma unroll
         for (int i = 0; i < 5; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[i * 8 + j] = __ldcg(p + j * 25 * RS + i * GW);
+          for (int j = 0; j < 8; ++j) v[i * 8 + j] = LOADFN(p + j * 25 * RS + i * GW);
 #pragma unroll
         for (int e = 0; e < 40; ++e) acc += v[e].x + v[e].y;
       }
@@ -34,7 +37,7 @@ template <int MODE> __global__ void __launch_bounds__(256, 1) pat(const float2* 
 #pragma unroll
         for (int i = 0; i < 5; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[i * 8 + j] = __ldcg(p + (j * 25 * 200 + i * 40) / 2);
+          for (int j = 0; j < 8; ++j) v[i * 8 + j] = LOADFN(p + (j * 25 * 200 + i * 40) / 2);
 #pragma unroll
         for (int e = 0; e < 40; ++e) acc += v[e].x + v[e].y + v[e].z + v[e].w;
       }
@@ -43,7 +46,7 @@ template <int MODE> __global__ void __launch_bounds__(256, 1) pat(const float2* 
       for (int k = 0; k < 2; ++k) {
         float4 v[40];
 #pragma unroll
-        for (int e = 0; e < 40; ++e) { const int idx = (k * 40 + e) * 256 + threadIdx.x; v[e] = idx < 20000 ? __ldcg(p + idx) : make_float4(0, 0, 0, 0); }
+        for (int e = 0; e < 40; ++e) { const int idx = (k * 40 + e) * 256 + threadIdx.x; v[e] = idx < 20000 ? LOADFN(p + idx) : make_float4(0, 0, 0, 0); }
 #pragma unroll
         for (int e = 0; e < 40; ++e) acc += v[e].x + v[e].y + v[e].z + v[e].w;
       }
@@ -51,7 +54,7 @@ template <int MODE> __global__ void __launch_bounds__(256, 1) pat(const float2* 
       for (int k = 0; k < 4; ++k) {
         float2 v[40];
 #pragma unroll
-        for (int e = 0; e < 40; ++e) { const int idx = (k * 40 + e) * 256 + threadIdx.x; v[e] = idx < 40000 ? __ldcg(img + idx) : make_float2(0, 0); }
+        for (int e = 0; e < 40; ++e) { const int idx = (k * 40 + e) * 256 + threadIdx.x; v[e] = idx < 40000 ? LOADFN(img + idx) : make_float2(0, 0); }
 #pragma unroll
         for (int e = 0; e < 40; ++e) acc += v[e].x + v[e].y;
       }
