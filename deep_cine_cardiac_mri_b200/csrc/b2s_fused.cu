@@ -12,7 +12,17 @@ namespace {
 typedef Plan<200, 200, 256, 1, 2> P200H;   // half split: 8 warps x 255 registers, 1 CTA/SM
 typedef Plan<200, 200, 128, 1, 4> P200Q;   // quarter split: 2 CTAs x 4 warps per SM
 typedef Plan<256, 256, 256, 1, 4> P256;    // quarter split, 1 CTA/SM
+typedef Plan<200, 200, 256, 2, 2, 1> P200W; // half split, 128-bit Phase A loads (two columns per thread)
 
+// B2S_WIDE: unset/-1 = auto (128-bit Phase A only where it measured faster: the two-stream sens_expand
+// without the DC epilogue, 148 vs 162 us), 0 = never, 1 = always.
+static int use_wide(int auto_on = 0) {
+  static int q = -2;
+  if (q == -2) { const char* e = getenv("B2S_WIDE"); q = e ? atoi(e) : -1; }
+  return q < 0 ? auto_on : q;
+}
+
+// B2S_SPLIT=4: quarter split with two 128-thread CTAs per SM (measured slower: 431 vs 330 us per DC step)
 static int use_quarter() {
   static int q = -1;
   if (q < 0) { const char* e = getenv("B2S_SPLIT"); q = (e && atoi(e) == 4) ? 1 : 0; }
@@ -73,8 +83,9 @@ int launch_pair(const Pro& pro, const Epi& epi, float scale, int64_t n_images, c
   return check_launch("fft2_pair_kernel");
 }
 
-// B2S_PAIR: unset/-1 = auto (paired kernel only where it measured faster: sens_expand without the DC
-// epilogue), 0 = never, 1 = always.  `auto_on` is the per-call-site default.
+// B2S_PAIR: 1 = use the paired (2-CTA cluster, DSMEM) kernel, otherwise not.  It halves the L2 -> SM ingest
+// of Phase A and measured 152 vs 162 us for the plain sens_expand, but the 128-bit Phase A (B2S_WIDE) is
+// faster still (148 us) and it loses for every other operator, so nothing selects it by default.
 static int use_pair(int auto_on = 0) {
   static int p = -2;
   if (p == -2) { const char* e = getenv("B2S_PAIR"); p = e ? atoi(e) : -1; }
@@ -92,12 +103,12 @@ int plan_fft2c(const float* in, float* out, int64_t n_images, int inverse, float
   if (inverse) {
     ProPlain<H, W, true> pro{(const cfloat*)in, hw};
     EpiPlain<H, W, true> epi{(cfloat*)out, hw};
-    if constexpr (P::FOLD == 2) { if (use_pair()) return launch_pair<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st); }
+    if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st); }
     return launch_fused<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st);
   }
   ProPlain<H, W, false> pro{(const cfloat*)in, hw};
   EpiPlain<H, W, false> epi{(cfloat*)out, hw};
-  if constexpr (P::FOLD == 2) { if (use_pair()) return launch_pair<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st); }
+  if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st); }
   return launch_fused<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st);
 }
 
@@ -111,7 +122,7 @@ int plan_expand(const float* image, const float* sens, float* kspace, const floa
 #define B2S_RUN(M)                                                                    \
   {                                                                                   \
     EpiKspace<H, W, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};      \
-    if constexpr (P::FOLD == 2) { if (use_pair(M != 2)) return launch_pair<P>(pro, epi, s, n, st); } \
+    if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
     return launch_fused<P>(pro, epi, s, n, st);                                       \
   }
   switch (mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) case 2: B2S_RUN(2) default: B2S_RUN(3) }
@@ -131,7 +142,7 @@ int plan_reduce(const float* kspace, const float* mult, float* out, const uint8_
 #define B2S_RUN(M)                                                      \
   {                                                                     \
     ProKspace<H, W, M> pro{(const cfloat*)kspace, mask, v, c, hw};      \
-    if constexpr (P::FOLD == 2) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
+    if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
     return launch_fused<P>(pro, epi, s, n, st);                         \
   }
   switch (weight_mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) default: B2S_RUN(2) }
@@ -173,7 +184,7 @@ extern "C" int b2s_fft2c(const float* in, float* out, int64_t n_images, int h, i
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = norm_scale(h, w, inverse, norm);
   switch (plan_id(h, w)) {
-    case 1: return use_quarter() ? plan_fft2c<P200Q>(in, out, n_images, inverse, scale, st) : plan_fft2c<P200H>(in, out, n_images, inverse, scale, st);
+    case 1: return use_wide() ? plan_fft2c<P200W>(in, out, n_images, inverse, scale, st) : use_quarter() ? plan_fft2c<P200Q>(in, out, n_images, inverse, scale, st) : plan_fft2c<P200H>(in, out, n_images, inverse, scale, st);
     case 2: return plan_fft2c<P256>(in, out, n_images, inverse, scale, st);
     default: return generic_fft2(in, out, n_images, h, w, inverse, scale, st);
   }
@@ -193,7 +204,8 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
   const int64_t n = (int64_t)b * t * c;
   const float scale = norm_scale(h, w, 0, norm);
   switch (plan_id(h, w)) {
-    case 1: return use_quarter() ? plan_expand<P200Q>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
+    case 1: return use_wide(mode != 2) ? plan_expand<P200W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
+                 : use_quarter() ? plan_expand<P200Q>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
                                  : plan_expand<P200H>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
     case 2: return plan_expand<P256>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
     default: break;
@@ -236,7 +248,8 @@ extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* ou
     B2S_CUDA(cudaMemsetAsync(out, 0, (size_t)out_images * hw * 2 * sizeof(float), st));
     if (n == 0) return B2S_OK;
     if (plan_id(h, w) == 2) return plan_reduce<P256>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
-    return use_quarter() ? plan_reduce<P200Q>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
+    return use_wide() ? plan_reduce<P200W>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
+         : use_quarter() ? plan_reduce<P200Q>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
                          : plan_reduce<P200H>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
   }
   // generic sizes: (row weight) -> IFFT into scratch -> conj-multiply + reduce

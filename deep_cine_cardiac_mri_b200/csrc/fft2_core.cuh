@@ -29,6 +29,7 @@
 
 // CTA barrier inside host/device phase code: the host emulation runs one phase for all thread ids in
 // turn, so there it is a no-op.
+#define B2S_OPAQUE(v) asm volatile("" : "+r"(v))
 #if defined(__CUDA_ARCH__)
 #define B2S_CTA_SYNC() __syncthreads()
 #else
@@ -60,12 +61,12 @@ B2S_HD cfloat twiddle(int n, int N) {
 // --------------------------------------------------------------------------- //
 // plans
 // --------------------------------------------------------------------------- //
-template <int H_, int W_, int NT_ = 256, int NC_ = 1, int FOLD_ = 2> struct Plan;
+template <int H_, int W_, int NT_ = 256, int NC_ = 1, int FOLD_ = 2, int NCC_ = NC_> struct Plan;
 
 // 200 x 200 (dataset crop, data/mri_data.py:273-277): h = 8*25, w = 5*40.
 // FOLD 2: half split, 170 KB of shared memory, one 256-thread CTA per SM.
 // FOLD 4: quarter split, 85 KB, two 128-thread CTAs per SM (their phases overlap) at the price of 4x L2 reads.
-template <int NT_, int NC_, int FOLD_> struct Plan<200, 200, NT_, NC_, FOLD_> {
+template <int NT_, int NC_, int FOLD_, int NCC_> struct Plan<200, 200, NT_, NC_, FOLD_, NCC_> {
   static constexpr int H = 200, W = 200;
   static constexpr int G = 25;        // Phase C codelet size, H = 8*G
   static constexpr int R = 5;         // Phase A column radix, W = R*X0
@@ -73,19 +74,20 @@ template <int NT_, int NC_, int FOLD_> struct Plan<200, 200, NT_, NC_, FOLD_> {
   static constexpr int SEG = 41;      // padded k1-segment pitch (complex) written by Phase A
   static constexpr int PITCH = 213;   // row pitch of B (complex); 213 = 5 mod 16 keeps Phase B conflict-free
   static constexpr int NT = NT_;      // threads per CTA
-  static constexpr int NC = NC_;      // adjacent columns per thread in Phases A and C (global access = 8*NC bytes)
+  static constexpr int NC = NC_;      // adjacent columns per thread in Phase A (global access = 8*NC bytes)
+  static constexpr int NCC = NCC_;    // ... and in Phase C
   static constexpr int FOLD = FOLD_;  // work items per image: item q produces output rows ky == q (mod FOLD)
   static constexpr int CTAS = (FOLD_ == 4) ? 2 : 1;   // resident CTAs per SM
 };
 
 // 256 x 256 (BASELINE.json configs[4]): h = 8*32, w = 8*32.  Half an image (128 x 256 complex) does not fit
 // in shared memory, so the image is split in four: item q keeps 2 of the 8 radix-8 outputs (ky == q mod 4).
-template <int NT_, int NC_, int FOLD_> struct Plan<256, 256, NT_, NC_, FOLD_> {
+template <int NT_, int NC_, int FOLD_, int NCC_> struct Plan<256, 256, NT_, NC_, FOLD_, NCC_> {
   static constexpr int H = 256, W = 256;
   static constexpr int G = 32, R = 8, X0 = 32;
   static constexpr int SEG = 33;      // 8 segments of 32 (+1 pad)
   static constexpr int PITCH = 265;   // odd: lanes along rows stay conflict-free in Phase B
-  static constexpr int NT = NT_, NC = NC_;
+  static constexpr int NT = NT_, NC = NC_, NCC = NCC_;
   static constexpr int FOLD = 4;
   static constexpr int CTAS = 1;
   static_assert(FOLD_ == 4, "256 x 256 only fits as a quarter split");
@@ -103,13 +105,13 @@ template <class P> struct Derived {
   static constexpr int SMEM_BYTES = SMEM_ELEMS * 8 + MASK_BYTES;
   static constexpr int XP = P::X0 / P::NC;                      // column groups per row group
   static constexpr int TASKS_A = P::G * XP;
-  static constexpr int KXP = P::W / P::NC;
+  static constexpr int KXP = P::W / P::NCC;
   static constexpr int TASKS_C = NKEEP * KXP;
   static constexpr int RPR = (P::NT / P::R) < ROWS ? (P::NT / P::R) : ROWS;   // rows per Phase-B round
   static constexpr int ROUNDS_B = (ROWS + RPR - 1) / RPR;
   static_assert(P::H == 8 * P::G && P::W == P::R * P::X0, "bad plan");
   static_assert((P::X0 & 1) == 0, "X0 must be even (sign folding)");
-  static_assert(P::X0 % P::NC == 0 && P::W % P::NC == 0, "NC must divide X0 and W");
+  static_assert(P::X0 % P::NC == 0 && P::W % P::NCC == 0, "NC must divide X0, NCC must divide W");
   static_assert(P::R * P::SEG <= P::PITCH && P::W <= P::PITCH, "pitch too small");
 };
 
@@ -147,7 +149,7 @@ template <class P, class Pro> struct PhaseA {
   static constexpr int TPT = (D::TASKS_A + NT - 1) / NT;       // tasks per thread and item
   static constexpr int STEPS = TPT * R;
   static constexpr int NK = D::NKEEP;
-  static constexpr int QD = Pro::template qdepth<R>();          // steps in flight
+  static constexpr int QD = Pro::template qdepth<R, false, NC>();   // steps in flight
   static_assert(STEPS % QD == 0 && (2 * R) % QD == 0 && TPT % 2 == 0, "queue depth must divide two tasks' steps");
   typedef typename Pro::template Unit<NC> Unit;
   struct Queue { Unit u[QD]; };
@@ -238,7 +240,9 @@ template <class P, class Pro> struct PhaseA {
         for (int r = 0; r < NK; ++r) th[r] = smem[D::TH_OFF + (q * G + g) * NK + r];
 #pragma unroll
         for (int n = 0; n < NC; ++n) {
-          const int x = x0 + n;
+          int x = x0 + n;
+          B2S_OPAQUE(x);                              // keep the twiddle addresses out of the persistent
+                                                      // loop's invariants (ptxas hoists and then spills them)
           const float sx = (x & 1) ? -1.f : 1.f;      // column parity of the input checkerboard
           cfloat tw[R];
 #pragma unroll
@@ -287,7 +291,7 @@ template <class P, class Pro> struct PhaseA2 {
   static constexpr int TASKS = G * XH;
   static constexpr int TPT = (TASKS + NT - 1) / NT;
   static constexpr int STEPS = TPT * R;
-  static constexpr int QD = Pro::template qdepth<R, true>();
+  static constexpr int QD = Pro::template qdepth<R, true, NC>();
   static_assert(STEPS % QD == 0 && (2 * R) % QD == 0 && TPT % 2 == 0, "queue depth must divide two tasks' steps");
   typedef typename Pro::template Unit<NC> Unit;
   struct Queue { Unit u[QD]; };
@@ -410,7 +414,7 @@ template <class P, class Epi>
 B2S_HD void phase_c(const Epi& epi, const typename Epi::Ctx& ctx, const cfloat* smem, int q, int task,
                     float scale) {
   using D = Derived<P>;
-  constexpr int G = P::G, NC = P::NC;
+  constexpr int G = P::G, NC = P::NCC;
   const int r = task / D::KXP, kx = (task - r * D::KXP) * NC;
   const int m = m_of<P>(r, q);
   const typename Epi::Ptr tp = epi.task_ptr(ctx, m, kx);   // rows m + 8*k: constant offsets 8*k*W

@@ -63,7 +63,7 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
     B2S_TICK(0);
     // warm L2 with the rest of the next item while this SM is busy with register codelets (Phases B, C)
     if (has_next && (next % P::FOLD) == 0) pro.l2_prefetch(next / P::FOLD, tid);
-    epi.l2_prefetch(image, q, tid);                        // what Phase C will read (issued here, not before
+    epi.l2_prefetch(image, q, P::FOLD, tid);                        // what Phase C will read (issued here, not before
                                                            // Phase A: bulk prefetches compete with its demand loads)
 
 #pragma unroll 1
@@ -78,6 +78,8 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
     }
 
     {
+      // (requesting a task's epilogue operands one task ahead, or behind the last Phase B write, was
+      // measured slower: sens_reduce 158 vs 140 us - the extra live registers cost more than the latency)
       const typename Epi::Ctx ectx = epi.ctx(image, mrow);
       for (int task = tid; task < D::TASKS_C; task += P::NT) phase_c<P>(epi, ectx, smem, q, task, scale);
     }
@@ -118,7 +120,7 @@ fft2_pair_kernel(const Pro pro, const Epi epi, const float scale, const int n_im
     cluster.sync();                                            // both halves of both B buffers written
     B2S_TICK(0);
     if (has_next && rank == 0) pro.l2_prefetch(next, tid);
-    epi.l2_prefetch(image, rank, tid);
+    epi.l2_prefetch(image, rank, 2, tid);
 
 #pragma unroll 1
     for (int round = 0; round < D::ROUNDS_B; ++round) {

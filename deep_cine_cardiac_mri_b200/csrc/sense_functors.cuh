@@ -102,7 +102,7 @@ template <int H, int W, bool INV> struct ProPlain {
   typedef const cfloat* Ptr;
   B2S_HD Ctx ctx(long long image) const { Ctx c; c.p = in + image * image_stride; return c; }
   // ~one task (32-40 loads) in flight per thread; the paired kernel holds both parities, so it keeps fewer
-  template <int R, bool PAIRED = false> static constexpr int qdepth() { return PAIRED ? 2 : (R <= 5 ? R : R / 2); }
+  template <int R, bool PAIRED = false, int NC = 1> static constexpr int qdepth() { return (PAIRED || NC > 1) ? 2 : (R <= 5 ? R : R / 2); }
   template <int NC> struct Unit { cvec<NC> a[8]; };
   // raw loads of the 8 rows g + G*j of one column group (row stride RS = G*W elements)
   template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int, int off, Unit<NC>& u) const {
@@ -132,7 +132,7 @@ template <int H, int W> struct ProExpand {
     const long long c = image % C, bt = image / C, b = bt / T;
     Ctx k; k.a = img + bt * hw; k.s = sens + (b * C + c) * hw; return k;
   }
-  template <int R, bool PAIRED = false> static constexpr int qdepth() { return PAIRED ? 1 : 2; }   // x 16 loads in flight per thread
+  template <int R, bool PAIRED = false, int NC = 1> static constexpr int qdepth() { return (PAIRED || NC > 1) ? 1 : 2; }   // x 16 loads in flight per thread
   template <int NC> struct Unit { cvec<NC> a[8], s[8]; };
   template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int, int off, Unit<NC>& u) const {
     const cfloat* pa = c.a + off; const cfloat* ps = c.s + off;
@@ -162,7 +162,7 @@ template <int H, int W, int WMODE> struct ProKspace {
     if (WMODE == 2) { const float v = *vptr; c.wb = -v / (1.f + v); }
     return c;
   }
-  template <int R, bool PAIRED = false> static constexpr int qdepth() { return PAIRED ? 2 : (R <= 5 ? R : R / 2); }
+  template <int R, bool PAIRED = false, int NC = 1> static constexpr int qdepth() { return (PAIRED || NC > 1) ? 2 : (R <= 5 ? R : R / 2); }
   template <int NC> struct Unit { cvec<NC> a[8]; float w[WMODE ? 8 : 1]; };
   template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int g, int off, Unit<NC>& u) const {
     const cfloat* p = c.p + off;
@@ -202,7 +202,7 @@ template <int H, int W, bool INV> struct EpiPlain {
 #endif
     stv<NC>(p + 8 * k * W, v);
   }
-  B2S_HD void l2_prefetch(long long, int, int) const {}
+  B2S_HD void l2_prefetch(long long, int, int, int) const {}
 };
 
 // MODE 0: k ; 1: k*m + 0.0 ; 2: (1-m) k + m (k + v ref)/(1+v) ; 3: k*m - ref
@@ -266,8 +266,14 @@ template <int H, int W, int MODE> struct EpiKspace {
     stv_stream<NC>(t.p + 8 * k * W, o);
   }
   // the reference k-space this item will blend with (whole image: the sibling half needs the rest)
-  B2S_HD void l2_prefetch(long long image, int q, int tid) const {
-    if (MODE >= 2 && q == 0) prefetch_span(ref + image * hw, (long long)H * W * 8, tid);
+  // DC (MODE 2) blends on sampled rows only: warm L2 with just those rows of this work item (ky = q mod
+  // fold), W*8 bytes each; MODE 3 reads every row.
+  B2S_HD void l2_prefetch(long long image, int q, int fold, int tid) const {
+    if (MODE == 3) { if (q == 0) prefetch_span(ref + image * hw, (long long)H * W * 8, tid); }
+    if (MODE == 2) {
+      const int y = fold * tid + q;
+      if (y < H && mask[(image / C) * H + y]) l2_prefetch_bulk(ref + image * hw + (long long)y * W, W * 8);
+    }
   }
 };
 
@@ -300,7 +306,7 @@ template <int H, int W> struct EpiReduce {
     }
     red_add<NC>(t.o + 8 * k * W, ar, ai);
   }
-  B2S_HD void l2_prefetch(long long, int, int) const {}
+  B2S_HD void l2_prefetch(long long, int, int, int) const {}
 };
 
 }  // namespace b2s

@@ -7,7 +7,8 @@
 
 using namespace b2s;
 typedef Plan<200, 200, 256, 1, 2> P200;    // half split
-typedef Plan<200, 200, 256, 2, 2> P200V;   // half split, 128-bit accesses
+typedef Plan<200, 200, 256, 2, 2> P200V;   // half split, 128-bit accesses in Phases A and C
+typedef Plan<200, 200, 256, 2, 2, 1> P200W; // half split, 128-bit Phase A only (what sens_expand ships)
 typedef Plan<200, 200, 128, 1, 4> P200Q;   // quarter split (2 CTAs/SM on the device)
 typedef Plan<256, 256, 256, 1, 4> P256;
 
@@ -20,7 +21,7 @@ static float norm_scale(int h, int w, int inverse, int norm) {
   return (float)s;
 }
 
-static int g_variant = 0;   // 200x200: 0 half split, 1 half split with 128-bit accesses, 2 quarter split, 3 paired (cluster)
+static int g_variant = 0;   // 200x200: 0 half split, 1 half split with 128-bit accesses, 2 quarter split, 3 paired (cluster), 4 wide Phase A
 #define EMULATE(P, pro, epi, scale, n) do { if (g_variant == 3 && P::FOLD == 2 && P::NC == 1) fft2_pair_emulate_if<P>(pro, epi, scale, n); else fft2_half_emulate<P>(pro, epi, scale, n); } while (0)
 template <class P, class Pro, class Epi> static void fft2_pair_emulate_if(const Pro& pro, const Epi& epi, float scale, long long n) {
   if constexpr (P::FOLD == 2 && P::NC == 1) fft2_pair_emulate<P>(pro, epi, scale, n); else fft2_half_emulate<P>(pro, epi, scale, n);
@@ -75,7 +76,7 @@ template <class P> static int t_reduce(const float* k, const float* mult, float*
 }
 
 #define DISPATCH(FN, ...)                                                          \
-  if (h == 200 && w == 200) return g_variant == 2 ? FN<P200Q>(__VA_ARGS__) : g_variant == 1 ? FN<P200V>(__VA_ARGS__) : FN<P200>(__VA_ARGS__); \
+  if (h == 200 && w == 200) return g_variant == 2 ? FN<P200Q>(__VA_ARGS__) : g_variant == 1 ? FN<P200V>(__VA_ARGS__) : g_variant == 4 ? FN<P200W>(__VA_ARGS__) : FN<P200>(__VA_ARGS__); \
   if (h == 256 && w == 256) return FN<P256>(__VA_ARGS__);                          \
   return 2;
 
