@@ -13,6 +13,7 @@ typedef Plan<200, 200, 256, 1, 2> P200H;   // half split: 8 warps x 255 register
 typedef Plan<200, 200, 128, 1, 4> P200Q;   // quarter split: 2 CTAs x 4 warps per SM
 typedef Plan<256, 256, 256, 1, 4> P256;    // quarter split, 1 CTA/SM
 typedef Plan<200, 200, 256, 2, 2, 1> P200W; // half split, 128-bit Phase A loads (two columns per thread)
+typedef Plan<256, 256, 256, 2, 4, 1> P256W; // quarter split, 128-bit Phase A loads
 
 // B2S_WIDE: unset/-1 = auto (128-bit Phase A only where it measured faster: the two-stream sens_expand
 // without the DC epilogue, 148 vs 162 us), 0 = never, 1 = always.
@@ -207,7 +208,8 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
     case 1: return use_wide(mode != 2) ? plan_expand<P200W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
                  : use_quarter() ? plan_expand<P200Q>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
                                  : plan_expand<P200H>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
-    case 2: return plan_expand<P256>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
+    case 2: return use_wide(1) ? plan_expand<P256W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
+                               : plan_expand<P256>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
     default: break;
   }
   // generic sizes: S*x -> kspace, FFT in place, epilogue in place

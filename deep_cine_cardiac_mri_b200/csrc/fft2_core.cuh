@@ -235,6 +235,7 @@ template <class P, class Pro> struct PhaseA {
         if (kp == 0) B2S_CTA_SYNC();           // the previous item's Phase C (its ragged last round overlaps
       }                                        // the loads issued above instead of idling 7 of 8 warps)
       if (i == R - 1 && valid) {
+        B2S_OPAQUE(g);                                // (same: table and B addresses stay per-task work)
         cfloat th[NK];
 #pragma unroll
         for (int r = 0; r < NK; ++r) th[r] = smem[D::TH_OFF + (q * G + g) * NK + r];

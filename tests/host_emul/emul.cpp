@@ -11,6 +11,7 @@ typedef Plan<200, 200, 256, 2, 2> P200V;   // half split, 128-bit accesses in Ph
 typedef Plan<200, 200, 256, 2, 2, 1> P200W; // half split, 128-bit Phase A only (what sens_expand ships)
 typedef Plan<200, 200, 128, 1, 4> P200Q;   // quarter split (2 CTAs/SM on the device)
 typedef Plan<256, 256, 256, 1, 4> P256;
+typedef Plan<256, 256, 256, 2, 4, 1> P256W;  // 128-bit Phase A (what sens_expand ships at 256 x 256)
 
 static float norm_scale(int h, int w, int inverse, int norm) {
   // norm: 0 "backward", 1 "ortho", 2 "forward" (torch.fft semantics)
@@ -77,7 +78,7 @@ template <class P> static int t_reduce(const float* k, const float* mult, float*
 
 #define DISPATCH(FN, ...)                                                          \
   if (h == 200 && w == 200) return g_variant == 2 ? FN<P200Q>(__VA_ARGS__) : g_variant == 1 ? FN<P200V>(__VA_ARGS__) : g_variant == 4 ? FN<P200W>(__VA_ARGS__) : FN<P200>(__VA_ARGS__); \
-  if (h == 256 && w == 256) return FN<P256>(__VA_ARGS__);                          \
+  if (h == 256 && w == 256) return g_variant == 4 ? FN<P256W>(__VA_ARGS__) : FN<P256>(__VA_ARGS__);                          \
   return 2;
 
 extern "C" {
