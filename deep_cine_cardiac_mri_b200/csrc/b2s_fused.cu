@@ -14,6 +14,7 @@ typedef Plan<200, 200, 128, 1, 4> P200Q;   // quarter split: 2 CTAs x 4 warps pe
 typedef Plan<256, 256, 256, 1, 4> P256;    // quarter split, 1 CTA/SM
 typedef Plan<200, 200, 256, 2, 2, 1> P200W; // half split, 128-bit Phase A loads (two columns per thread)
 typedef Plan<256, 256, 256, 2, 4, 1> P256W; // quarter split, 128-bit Phase A loads
+constexpr int W256_PLAIN = 0;               // auto choice of P256W for fft2c / sens_reduce (sens_expand: always)
 
 // B2S_WIDE: unset/-1 = auto (128-bit Phase A only where it measured faster: the two-stream sens_expand
 // without the DC epilogue, 148 vs 162 us), 0 = never, 1 = always.
@@ -186,7 +187,7 @@ extern "C" int b2s_fft2c(const float* in, float* out, int64_t n_images, int h, i
   const float scale = norm_scale(h, w, inverse, norm);
   switch (plan_id(h, w)) {
     case 1: return use_wide() ? plan_fft2c<P200W>(in, out, n_images, inverse, scale, st) : use_quarter() ? plan_fft2c<P200Q>(in, out, n_images, inverse, scale, st) : plan_fft2c<P200H>(in, out, n_images, inverse, scale, st);
-    case 2: return plan_fft2c<P256>(in, out, n_images, inverse, scale, st);
+    case 2: return use_wide(W256_PLAIN) ? plan_fft2c<P256W>(in, out, n_images, inverse, scale, st) : plan_fft2c<P256>(in, out, n_images, inverse, scale, st);
     default: return generic_fft2(in, out, n_images, h, w, inverse, scale, st);
   }
 }
@@ -249,7 +250,8 @@ extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* ou
   if (plan_id(h, w)) {
     B2S_CUDA(cudaMemsetAsync(out, 0, (size_t)out_images * hw * 2 * sizeof(float), st));
     if (n == 0) return B2S_OK;
-    if (plan_id(h, w) == 2) return plan_reduce<P256>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
+    if (plan_id(h, w) == 2) return use_wide(W256_PLAIN) ? plan_reduce<P256W>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
+                                                       : plan_reduce<P256>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
     return use_wide() ? plan_reduce<P200W>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
          : use_quarter() ? plan_reduce<P200Q>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
                          : plan_reduce<P200H>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
