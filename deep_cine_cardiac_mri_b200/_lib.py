@@ -47,8 +47,14 @@ SIGNATURES = {
     "b2s_axpby": [_p, _p, _p, _f, _p, _i64, _p],
     "b2s_dc_step_ws_bytes": [_i, _i, _i, _i, _i],
     "b2s_dc_step_host": [_p, _p, _p, _p, _f, _p, _i, _i, _i, _i, _i, _p, _sz, _p],
+    "b2s_ssim_scratch_floats": [_i, _i, _i, _i],
+    "b2s_ssim_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
+    "b2s_ssim_bwd": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p],
+    "b2s_frame_max": [_p, _p, _i, _i, _i64, _p],
+    "b2s_err_stats": [_p, _p, _i64, _p, _p, _p],
 }
-_RESTYPE = {"b2s_launch_count": C.c_ulonglong, "b2s_last_error": C.c_char_p, "b2s_scratch_bytes": _sz, "b2s_dc_step_ws_bytes": _sz}
+_RESTYPE = {"b2s_launch_count": C.c_ulonglong, "b2s_last_error": C.c_char_p, "b2s_scratch_bytes": _sz, "b2s_dc_step_ws_bytes": _sz,
+            "b2s_ssim_scratch_floats": _sz}
 
 
 def build(verbose: bool = False) -> Path:

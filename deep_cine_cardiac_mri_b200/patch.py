@@ -124,7 +124,20 @@ def patch_reference(functional: bool = True, block_methods: bool = True):
     _set(rcin.CineNet_RNN, "sens_reduce", blocks.sens_reduce)
     _set(rcin.CineNet_RNN, "HOperator", blocks.h_operator)
     _set(rcin.CineNet_RNN, "ConjGrad", blocks.conj_grad)
+
+    # training loss (utils/losses.py:25-58): same module, same buffer; forward on the fused SSIM kernels
+    try:
+        losses = importlib.import_module("reconstruction.utils.losses")
+    except ImportError:
+        losses = None
+    if losses is not None and hasattr(losses, "SSIMLoss"):
+        _set(losses.SSIMLoss, "forward", _ssim_loss_forward)
     return models
+
+
+def _ssim_loss_forward(self, Xt, Yt, data_range=None):
+    from . import metrics
+    return metrics.ssim_loss(Xt, Yt, self.win_size, self.k1, self.k2)
 
 
 def unpatch_reference():

@@ -161,6 +161,28 @@ int b2s_dc_step_host(const float* kspace_host, const float* ref_host, const floa
                      const uint8_t* mask_host, float v_value, float* out_host, int b, int t, int c,
                      int h, int w, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- training loss and test metrics -------------------------------------------- *
+ * Time-averaged SSIM - utils/losses.py:25-58 (SSIMLoss.forward) and utils/evaluate.py:25-42 (ssim):
+ * x, y (b,t,h,w) float32; `win` x `win` uniform window (only 7 is built), "valid" positions, sample
+ * covariance; data_range[(frame index t) * dr_stride] read from device memory (dr_stride 1: one value per
+ * frame t, as the loss takes Y.max() per frame; 0: one value for the whole volume, as the metric does).
+ * out[0..t-1] = mean S of frame t over batch and window positions, out[t] = mean_t (1 - out[t]) = the loss.
+ * scratch: b2s_ssim_scratch_floats() floats.  Ordered sums: bit-reproducible. */
+size_t b2s_ssim_scratch_floats(int b, int t, int h, int w);
+int b2s_ssim_fwd(const float* x, const float* y, const float* data_range, int dr_stride, int b, int t,
+                 int h, int w, int win, float k1, float k2, float* out, float* scratch, void* stream);
+/* gx = gout[0] * d out[t] / d x  (the loss's gradient w.r.t. the prediction; y and data_range are constants,
+ * as in the reference where data_range is rebuilt from a Python float, losses.py:35) */
+int b2s_ssim_bwd(const float* x, const float* y, const float* data_range, int dr_stride,
+                 const float* gout, int b, int t, int h, int w, int win, float k1, float k2, float* gx,
+                 void* stream);
+/* out[t] = max over batch and pixels of frame t of y (b,t,hw) - the loss's data_range (losses.py:35) */
+int b2s_frame_max(const float* y, float* out, int b, int t, int64_t hw, void* stream);
+/* out[0] = sum (gt-pred)^2, out[1] = sum gt^2, out[2] = max gt, out[3] = n  over n floats (ordered two-stage
+ * sums; scratch >= 3072 floats): NMSE = out[0]/out[1], PSNR = 10 log10(maxval^2 n / out[0]) -
+ * utils/evaluate.py:6-22 */
+int b2s_err_stats(const float* gt, const float* pred, int64_t n, float* out, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -377,3 +377,30 @@ def ssim(gt, pred, maxval=None, win=7, k1=0.01, k2=0.03):
         s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
         tot += s.mean()
     return tot / gt.shape[0]
+
+
+def ssim_loss(Xt, Yt, win=7, k1=0.01, k2=0.03):
+    """SSIMLoss.forward, utils/losses.py:25-58: Xt, Yt (b,1,t,h,w); per frame t the data range is the maximum
+    of the target frame over the WHOLE batch (`torch.Tensor([Y.max()])`, :35 - the `data_range` argument is
+    overwritten), S from five win x win uniform 'valid' convolutions with the sample-covariance factor
+    NP/(NP-1), loss = mean_t (1 - mean S).  Returns (loss, per-frame mean S), fp64."""
+    Xt = np.asarray(Xt, dtype=np.float64)
+    Yt = np.asarray(Yt, dtype=np.float64)
+    cov_norm = win * win / (win * win - 1)
+    nt = Xt.shape[2]
+    means = np.zeros(nt)
+    for t in range(nt):
+        data_range = Yt[:, :, t].max()
+        c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+        acc, cnt = 0.0, 0
+        for b in range(Xt.shape[0]):
+            x, y = Xt[b, 0, t], Yt[b, 0, t]
+            ux, uy = _box7(x, win), _box7(y, win)
+            vx = cov_norm * (_box7(x * x, win) - ux * ux)
+            vy = cov_norm * (_box7(y * y, win) - uy * uy)
+            vxy = cov_norm * (_box7(x * y, win) - ux * uy)
+            s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+            acc += s.sum()
+            cnt += s.size
+        means[t] = acc / cnt
+    return float(np.mean(1.0 - means)), means

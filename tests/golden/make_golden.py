@@ -188,5 +188,61 @@ def main():
           f"({(HERE/'golden_v1.npz').stat().st_size/1e6:.2f} MB)")
 
 
+# --------------------------------------------------------------------------- #
+# SSIM loss (utils/losses.py) - second fixture file, golden_v2_loss.npz
+# --------------------------------------------------------------------------- #
+LOSS_CASES = {"a": (2, 3, 40, 36), "one": (1, 1, 7, 9), "full": (1, 15, 200, 200)}   # (b, t, h, w)
+
+
+def loss_case(name):
+    """Seeded (prediction, target) pair with the statistics of magnitude images: target = |smooth + noise|,
+    prediction = target + small error.  Shapes (b, t, h, w) float32."""
+    b, t, h, w = LOSS_CASES[name]
+    seed = 900 + sorted(LOSS_CASES).index(name)
+    tgt = np.abs(rng_normal(seed, (b, t, h, w)) + 2.0 * np.sin(np.arange(w, dtype=np.float32) / 7.0)).astype(np.float32)
+    pred = (tgt + 0.1 * rng_normal(seed + 50, (b, t, h, w))).astype(np.float32)
+    return pred, tgt
+
+
+def main_loss():
+    """Runs the reference's own SSIMLoss (forward and autograd) on the CPU; its hard-coded `.to('cuda')`
+    (losses.py:35) is neutralised for the duration of the call."""
+    import torch
+    rec, _ = _load_reference()
+    from reconstruction.utils.losses import SSIMLoss
+    orig_to = torch.Tensor.to
+
+    def to_cpu(self, *a, **k):
+        a = tuple(x for x in a if not (isinstance(x, str) and x.startswith("cuda")))
+        return orig_to(self, *a, **k) if (a or k) else self
+
+    out = {}
+    torch.Tensor.to = to_cpu
+    try:
+        for name in LOSS_CASES:
+            pred, tgt = loss_case(name)
+            for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+                x = torch.from_numpy(pred).to(dt).unsqueeze(1).requires_grad_(True)      # (b,1,t,h,w) as varnet_module.py:110-112
+                y = torch.from_numpy(tgt).to(dt).unsqueeze(1)
+                mod = SSIMLoss().to(dt)
+                # losses.py:35 builds data_range with torch.Tensor([...]) (float32); promote it in the f64 run
+                loss = mod(x, y, data_range=torch.tensor([float(tgt.max())]))
+                loss.backward()
+                out[f"{name}/{tag}/loss"] = np.asarray(loss.detach().numpy())
+                g = x.grad.squeeze(1).numpy()
+                if g.size > 50000:
+                    idx = sample_index(g.size)
+                    out[f"{name}/{tag}/grad_sample"] = g.reshape(-1)[idx]
+                else:
+                    out[f"{name}/{tag}/grad"] = g
+    finally:
+        torch.Tensor.to = orig_to
+    np.savez_compressed(HERE / "golden_v2_loss.npz", **out)
+    print(f"wrote {len(out)} arrays -> {HERE/'golden_v2_loss.npz'}")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "loss":
+        main_loss()
+    else:
+        main()

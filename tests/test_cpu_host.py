@@ -276,6 +276,7 @@ def _fake_reference(tmp_path):
         (pkg / "models" / f"{mod}.py").write_text("".join(
             f"class {c}:\n    def forward(self, *a):\n        return 'reference'\n    def sens_expand(self, *a):\n        return 'reference'\n" for c in classes))
     (pkg / "models" / "__init__.py").write_text("")
+    (pkg / "utils" / "losses.py").write_text("class SSIMLoss:\n    def forward(self, *a):\n        return 'reference'\n")
     return pkg
 
 
@@ -296,10 +297,12 @@ def test_patch_and_unpatch_reference(tmp_path, monkeypatch):
         assert V.VarNetBlock.sens_expand is blocks.sens_expand
         assert X.ForwardOperator.forward is blocks.forward_operator_forward
         assert hasattr(X.XPDNetBlock, "xfyf_transform")
+        import reconstruction.utils.losses as L
+        assert L.SSIMLoss.forward is patch._ssim_loss_forward
         assert patch.is_patched()
     finally:
         patch.unpatch_reference()
-    assert U.fft2c() == "reference" and V.VarNetBlock().forward() == "reference"
+    assert U.fft2c() == "reference" and V.VarNetBlock().forward() == "reference" and L.SSIMLoss().forward() == "reference"
     assert not hasattr(X.XPDNetBlock, "xfyf_transform") and not patch.is_patched()
 
 

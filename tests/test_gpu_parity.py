@@ -603,3 +603,53 @@ def test_deterministic_mode_is_bit_reproducible(ops, hw):
     finally:
         ops.set_deterministic(False)
     assert all(torch.equal(u, v_) for u, v_ in zip(a, c3))
+
+
+# ------------------------------- loss and metrics ------------------------- #
+@pytest.mark.parametrize("name", sorted(G.LOSS_CASES))
+def test_ssim_loss_matches_reference(name):
+    """metrics.SSIMLoss (fused kernels, no host sync) vs the fp64 oracle and the reference's own outputs
+    (golden_v2_loss.npz): |d loss| <= 1e-6 (S is O(1): 1e-6 of its scale), gradient <= 2e-5 of max|grad|."""
+    from pathlib import Path
+    from deep_cine_cardiac_mri_b200 import metrics
+    z = np.load(Path(__file__).parent / "golden" / "golden_v2_loss.npz")
+    pred, tgt = G.loss_case(name)
+    x = cu(pred).unsqueeze(1).requires_grad_(True)
+    y = cu(tgt).unsqueeze(1)
+    mod = metrics.SSIMLoss().cuda()
+    assert tuple(mod.state_dict()["w"].shape) == (1, 1, 7, 7)            # checkpoint-compatible buffer
+    loss = mod(x, y, data_range=torch.tensor([123.0]))                   # argument ignored, as in the reference
+    want, _ = O.ssim_loss(pred[:, None], tgt[:, None])
+    assert abs(float(loss.detach()) - want) <= 1e-6, (float(loss.detach()), want)
+    assert abs(float(loss.detach()) - float(z[f"{name}/f64/loss"])) <= 1e-6
+    (loss * 3.0).backward()
+    g = x.grad[:, 0].cpu().numpy() / 3.0
+    if f"{name}/f64/grad" in z.files:
+        ref = z[f"{name}/f64/grad"]
+    else:
+        ref, g = z[f"{name}/f64/grad_sample"], g.reshape(-1)[G.sample_index(g.size)]
+    assert np.abs(g - ref).max() <= 2e-5 * np.abs(ref).max(), np.abs(g - ref).max() / np.abs(ref).max()
+    x2 = cu(pred).unsqueeze(1).requires_grad_(True)
+    l2 = mod(x2, y)
+    (l2 * 3.0).backward()
+    assert torch.equal(l2.detach(), loss.detach()) and torch.equal(x2.grad, x.grad)  # ordered sums: reproducible
+
+
+def test_evaluation_metrics_match_oracle():
+    """metrics.{mse,nmse,psnr,ssim} (utils/evaluate.py:6-49) on device tensors vs the oracle, 1e-5 relative."""
+    from deep_cine_cardiac_mri_b200 import metrics
+    pred, tgt = G.loss_case("full")
+    gt, pr = tgt[0], pred[0]                                              # (t,h,w)
+    dgt, dpr = cu(gt), cu(pr)
+    for got, want in ((metrics.nmse(dgt, dpr), O.nmse(f64(gt), f64(pr))), (metrics.psnr(dgt, dpr), O.psnr(gt, pr)),
+                      (metrics.psnr(dgt, dpr, maxval=3.5), O.psnr(gt, pr, 3.5)), (metrics.ssim(dgt, dpr), O.ssim(gt, pr)),
+                      (metrics.ssim(dgt, dpr, maxval=4.0), O.ssim(gt, pr, 4.0)),
+                      (metrics.mse(dgt, dpr), float(np.mean((f64(gt) - f64(pr)) ** 2)))):
+        assert got.is_cuda and got.dim() == 0
+        assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want)), (float(got), float(want))
+    with pytest.raises(ValueError, match="Unexpected number of dimensions in ground truth."):
+        metrics.ssim(dgt[0], dpr[0])
+    with pytest.raises(ValueError, match="Ground truth dimensions does not match pred."):
+        metrics.ssim(dgt, dpr[0])
+    with pytest.raises(RuntimeError):
+        metrics.nmse(torch.zeros(4), torch.zeros(4))                      # CPU tensors: no fallback

@@ -1,5 +1,7 @@
 """Pin the numpy oracle against fixtures produced by the reference's own torch
 code (tests/golden/make_golden.py).  CPU only."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -109,3 +111,19 @@ def test_acs_window_default_mask():
     m[0, 0, 0, 90:95] = 0
     m[0, 0, 0, 105:110] = 0
     assert O.acs_window(m) == (95, 11)
+
+
+@pytest.mark.parametrize("name", sorted(G.LOSS_CASES))
+def test_ssim_loss_oracle_matches_reference_golden(name):
+    """oracle.ssim_loss (fp64 restatement of utils/losses.py:25-58) vs the reference's own SSIMLoss run in
+    fp64 and fp32 (tests/golden/make_golden.py loss)."""
+    z = np.load(Path(__file__).parent / "golden" / "golden_v2_loss.npz")
+    pred, tgt = G.loss_case(name)
+    loss, means = O.ssim_loss(pred[:, None], tgt[:, None])
+    assert abs(loss - float(z[f"{name}/f64/loss"])) <= 1e-9
+    assert abs(loss - float(z[f"{name}/f32/loss"])) <= 5e-6          # the reference's own fp32 noise
+    assert means.shape == (pred.shape[1],)
+    # evaluate.py's ssim is the same formula with one data range per volume
+    if pred.shape[2] >= 7:
+        v = O.ssim(tgt[0], pred[0])
+        assert 0.0 < v <= 1.0
