@@ -47,6 +47,7 @@ SIGNATURES = {
     "b2s_axpby": [_p, _p, _p, _f, _p, _i64, _p],
     "b2s_dc_step_ws_bytes": [_i, _i, _i, _i, _i],
     "b2s_dc_step_host": [_p, _p, _p, _p, _f, _p, _i, _i, _i, _i, _i, _p, _sz, _p],
+    "b2s_upload_rows": [_p, _p, _p, _i64, _i, _i, _i, _p],
     "b2s_ssim_scratch_floats": [_i, _i, _i, _i],
     "b2s_ssim_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
     "b2s_ssim_bwd": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p],

@@ -89,6 +89,31 @@ __global__ void coil_reduce_kernel(const cfloat* y, const cfloat* mult, cfloat* 
   }
 }
 
+// ------------------------- sparse upload of masked k-space ------------------ //
+// One warp per k-space row: sampled rows (mask = 1) are read straight from pinned host memory (UVA: the
+// host pointer is valid on the device) and land in the dense device tensor, unsampled rows are written as
+// zeros.  Only the sampled quarter of the k-space crosses PCIe, and no host thread packs anything.
+template <class V>
+__global__ void upload_rows_kernel(const V* __restrict__ src, const uint8_t* __restrict__ mask, V* __restrict__ dst, int C, int H,
+                                   int WV, long long n_rows) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < n_rows; row += (long long)gridDim.x * wpb) {
+    const long long bt = row / ((long long)C * H);
+    const int y = (int)(row % H);
+    const bool m = mask[bt * H + y] != 0;
+    const V* s = src + row * WV;
+    V* d = dst + row * WV;
+    V zero; memset(&zero, 0, sizeof(V));
+    for (int i0 = 0; i0 < WV; i0 += 128) {                 // 4 independent host reads per lane in flight
+      V v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + lane + 32 * u; v[u] = (m && i < WV) ? s[i] : zero; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + lane + 32 * u; if (i < WV) d[i] = v[u]; }
+    }
+  }
+}
+
 // ------------------------------- DC blend ---------------------------------- //
 // V = float4 (two complex per thread, even w) or cfloat (odd w)
 template <class V> struct VecOps;
@@ -417,6 +442,27 @@ int launch_coil_reduce(const float* y, const float* mult, float* out, int over_f
 }
 
 }  // namespace b2s
+
+extern "C" int b2s_upload_rows(const float* kspace_host, const uint8_t* mask, float* kspace_dev, int64_t n_bt, int c, int h,
+                               int w, void* stream) {
+  if (n_bt < 0 || c < 0 || h < 0 || w < 0) return fail(B2S_EINVAL, "b2s_upload_rows: bad argument");
+  const long long n_rows = n_bt * c * (long long)h;
+  if (n_rows == 0 || w == 0) return B2S_OK;
+  if (!kspace_host || !mask || !kspace_dev) return fail(B2S_EINVAL, "b2s_upload_rows: null pointer");
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, kspace_host) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+    cudaGetLastError();
+    return fail(B2S_EINVAL, "b2s_upload_rows: kspace_host must be pinned (page-locked, device-accessible) host memory");
+  }
+  const float* src = (const float*)attr.devicePointer;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = 148 * 8;
+  if (w % 2 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)kspace_dev % 16 == 0))
+    upload_rows_kernel<float4><<<grid, NT, 0, st>>>((const float4*)src, mask, (float4*)kspace_dev, c, h, w / 2, n_rows);
+  else
+    upload_rows_kernel<float2><<<grid, NT, 0, st>>>((const float2*)src, mask, (float2*)kspace_dev, c, h, w, n_rows);
+  return check_launch("upload_rows_kernel");
+}
 
 extern "C" int b2s_dc_blend(const float* kspace, const float* ref, const uint8_t* mask, const float* v, float* out,
                             int64_t n_bt, int c, int h, int w, void* stream) {

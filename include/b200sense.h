@@ -161,6 +161,12 @@ int b2s_dc_step_host(const float* kspace_host, const float* ref_host, const floa
                      const uint8_t* mask_host, float v_value, float* out_host, int b, int t, int c,
                      int h, int w, void* ws, size_t ws_bytes, void* stream);
 
+/* Sparse upload of a masked k-space (what data/transforms.py:66-92 apply_mask leaves: unsampled rows are
+ * zero).  kspace_host: PINNED host memory (n_bt,c,h,w,2), read by the GPU over PCIe (UVA); only rows with
+ * mask (n_bt,h) != 0 are transferred, the others are written as zeros into kspace_dev.  mask: device. */
+int b2s_upload_rows(const float* kspace_host, const uint8_t* mask, float* kspace_dev, int64_t n_bt, int c,
+                    int h, int w, void* stream);
+
 /* ---- training loss and test metrics -------------------------------------------- *
  * Time-averaged SSIM - utils/losses.py:25-58 (SSIMLoss.forward) and utils/evaluate.py:25-42 (ssim):
  * x, y (b,t,h,w) float32; `win` x `win` uniform window (only 7 is built), "valid" positions, sample
