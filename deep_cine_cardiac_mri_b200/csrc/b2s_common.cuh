@@ -42,6 +42,17 @@ inline bool bad_norm(int norm) { return norm < 0 || norm > 2; }
 int generic_fft2(const float* in, float* out, int64_t n_images, int h, int w, int inverse, float scale,
                  cudaStream_t st);
 
+// strip-streamed fused kernels (b2s_strip.cu), h == w in {200, 256}.  `*unavailable` = 1 (and B2S_OK) when the
+// launch could not be made (stream capturing before the workspace exists): the caller uses the on-chip kernels.
+int use_strip();
+int strip_fft2c(int h, const float* in, float* out, int64_t n, int inverse, float scale, cudaStream_t st, int* unavailable);
+int strip_expand(int h, const float* image, const float* sens, float* kspace, const float* ref, const uint8_t* mask,
+                 const float* v, int mode, int t, int c, int64_t n, float scale, cudaStream_t st, int* unavailable);
+int strip_reduce(int h, const float* kspace, const float* mult, float* out, const uint8_t* mask, const float* v,
+                 int weight_mode, int over_frames, int t, int c, int64_t n, float scale, cudaStream_t st, int* unavailable);
+int strip_ifft_weighted(int h, const float* kspace, float* y, const uint8_t* mask, const float* v, int weight_mode, int c,
+                        int64_t n, float scale, cudaStream_t st, int* unavailable);
+
 // element-wise helpers used by the non-fused fallbacks (b2s_pointwise.cu)
 int launch_expand_product(const float* image, const float* sens, float* out, int b, int t, int c,
                           int64_t hw, cudaStream_t st);

@@ -185,6 +185,11 @@ extern "C" int b2s_fft2c(const float* in, float* out, int64_t n_images, int h, i
   if (!in || !out) return fail(B2S_EINVAL, "b2s_fft2c: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = norm_scale(h, w, inverse, norm);
+  if (plan_id(h, w) && use_strip()) {
+    int un = 0;
+    const int rc = strip_fft2c(h, in, out, n_images, inverse, scale, st, &un);
+    if (rc || !un) return rc;
+  }
   switch (plan_id(h, w)) {
     case 1: return use_wide() ? plan_fft2c<P200W>(in, out, n_images, inverse, scale, st) : use_quarter() ? plan_fft2c<P200Q>(in, out, n_images, inverse, scale, st) : plan_fft2c<P200H>(in, out, n_images, inverse, scale, st);
     case 2: return use_wide(W256_PLAIN) ? plan_fft2c<P256W>(in, out, n_images, inverse, scale, st) : plan_fft2c<P256>(in, out, n_images, inverse, scale, st);
@@ -205,6 +210,11 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = (int64_t)b * t * c;
   const float scale = norm_scale(h, w, 0, norm);
+  if (plan_id(h, w) && use_strip()) {
+    int un = 0;
+    const int rc = strip_expand(h, image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st, &un);
+    if (rc || !un) return rc;
+  }
   switch (plan_id(h, w)) {
     case 1: return use_wide(mode != 2) ? plan_expand<P200W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
                  : use_quarter() ? plan_expand<P200Q>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
@@ -242,6 +252,12 @@ extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* ou
     const size_t need = (size_t)n * hw * 2 * sizeof(float);
     if (!scratch || scratch_bytes < need) return fail(B2S_EINVAL, "b2s_sens_reduce: deterministic mode needs b*t*c*h*w*8 scratch bytes");
     float* y = (float*)scratch;
+    if (use_strip()) {
+      int un = 0;
+      const int rcs = strip_ifft_weighted(h, kspace, y, mask, v, weight_mode, c, n, scale, st, &un);
+      if (rcs) return rcs;
+      if (!un) return launch_coil_reduce(y, mult, out, over_frames, b, t, c, hw, st);
+    }
     const int rc = plan_id(h, w) == 2 ? plan_ifft_weighted<P256>(kspace, y, mask, v, weight_mode, c, n, scale, st)
                                       : plan_ifft_weighted<P200H>(kspace, y, mask, v, weight_mode, c, n, scale, st);
     if (rc) return rc;
@@ -250,6 +266,11 @@ extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* ou
   if (plan_id(h, w)) {
     B2S_CUDA(cudaMemsetAsync(out, 0, (size_t)out_images * hw * 2 * sizeof(float), st));
     if (n == 0) return B2S_OK;
+    if (use_strip()) {
+      int un = 0;
+      const int rcs = strip_reduce(h, kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st, &un);
+      if (rcs || !un) return rcs;
+    }
     if (plan_id(h, w) == 2) return use_wide(W256_PLAIN) ? plan_reduce<P256W>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
                                                        : plan_reduce<P256>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
     return use_wide() ? plan_reduce<P200W>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)

@@ -93,6 +93,36 @@ def deterministic() -> bool:
     return _force_deterministic or torch.are_deterministic_algorithms_enabled()
 
 
+def set_fused_path(path) -> None:
+    """Implementation behind the fused plan sizes (200x200, 256x256): "onchip" (half/quarter-split kernels, default),
+    "strip" (two passes through an L2-resident scratch ring) or None (environment: B2S_PATH=strip|half)."""
+    code = {None: -1, "onchip": 0, "half": 0, "strip": 1}[path]
+    _lib.check(_lib.lib().b2s_set_fused_path(code), "set_fused_path")
+
+
+def strip_status() -> int:
+    """0 when no inter-CTA dependency wait of the strip kernels ever timed out on the current device (synchronises)."""
+    return int(_lib.lib().b2s_debug_strip_status())
+
+
+def upload_masked_kspace(kspace_host: torch.Tensor, mask_dev: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """Sparse host->device upload of a masked k-space (what data/transforms.py:66-92 apply_mask leaves: unsampled
+    rows are zero).  `kspace_host` (b,t,c,h,w,2) float32 in PINNED host memory, `mask_dev` the (b,t,1,h,1,1) / (b,t,h)
+    uint8 mask already on the device.  Only the sampled rows cross PCIe (the GPU reads them in place over UVA), the
+    others are written as zeros; runs on the current stream."""
+    if kspace_host.is_cuda or not kspace_host.is_pinned():
+        raise ValueError("upload_masked_kspace: kspace_host must be a pinned host tensor")
+    if kspace_host.dtype != torch.float32 or kspace_host.dim() != 6 or kspace_host.shape[-1] != 2 or not kspace_host.is_contiguous():
+        raise ValueError("upload_masked_kspace: kspace_host must be contiguous float32 (b,t,c,h,w,2)")
+    _need_cuda(mask_dev)
+    b, t, c, h, w, _ = kspace_host.shape
+    m = _mask_u8(mask_dev, b, t, h)
+    if out is None:
+        out = torch.empty(kspace_host.shape, dtype=torch.float32, device=mask_dev.device)
+    _lib.check(_lib.lib().b2s_upload_rows(C.c_void_p(kspace_host.data_ptr()), _p(m), _p(out), b * t, c, h, w, _stream()), "upload_rows")
+    return out
+
+
 def _scratch_for(b, t, c, h, w, device, full=False):
     n = b * t * c * h * w * 8 if full else _lib.lib().b2s_scratch_bytes(b, t, c, h, w)
     if n == 0:

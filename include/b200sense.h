@@ -56,6 +56,14 @@ int b2s_version(void);
 const char* b2s_last_error(void);
 /* number of CUDA kernels this library has launched so far (host-side counter; reset != 0 zeroes it) */
 unsigned long long b2s_launch_count(int reset);
+/* Diagnostic of the strip-streamed kernels (csrc/strip_core.cuh): synchronises the current device and returns 0 when
+ * no inter-CTA dependency wait ever timed out on it (non-zero = results of that launch are invalid; -1 = CUDA error). */
+int b2s_debug_strip_status(void);
+/* Selects the implementation behind the fused plan sizes (200x200, 256x256) of b2s_fft2c / b2s_sens_expand /
+ * b2s_sens_reduce: 0 = on-chip half/quarter-split kernels (default), 1 = strip-streamed kernels (two passes through
+ * an L2-resident scratch ring, csrc/strip_core.cuh), -1 = re-read the environment (B2S_PATH=strip|half).  Both compute
+ * the same operators (same parity tests); process-wide. */
+int b2s_set_fused_path(int path);
 /* 1 if (h,w) runs on the fused single-pass kernels, 0 if on the generic two-pass ones */
 int b2s_has_fused_plan(int h, int w);
 /* bytes of scratch b2s_sens_expand / b2s_sens_reduce need for this shape (0 for fused plans) */

@@ -127,8 +127,19 @@ def make_case(tag):
     return cs, {k: (f64(v) if getattr(v, "dtype", None) == np.float32 and v.ndim else v) for k, v in cs.items()}
 
 
+@pytest.fixture(params=["onchip", "strip"])
+def fused_path(request, ops):
+    """Run the test once per implementation of the fused plan sizes: the on-chip half/quarter-split kernels and the
+    strip-streamed kernels (b2s_set_fused_path); the strip run also checks that no dependency wait timed out."""
+    ops.set_fused_path(request.param)
+    yield request.param
+    if request.param == "strip":
+        assert ops.strip_status() == 0
+    ops.set_fused_path(None)
+
+
 @pytest.mark.parametrize("tag", list(CASES))
-def test_sens_expand_reduce_dc(ops, tag):
+def test_sens_expand_reduce_dc(ops, tag, fused_path):
     cs, d = make_case(tag)
     img, k, ref, sens, mask = (cu(cs[n]) for n in ("img", "k", "ref", "sens", "mask"))
     v = float(O.softplus(cs["lam"]))
@@ -377,7 +388,7 @@ def test_against_reference_golden(ops, F, tag):
 
 # ----------------------- size-independent properties at full size ----------- #
 @pytest.mark.parametrize("cfg", [(4, 15, 10, 200, 200), (1, 25, 20, 200, 200)])
-def test_properties_full_size(ops, F, cfg):
+def test_properties_full_size(ops, F, cfg, fused_path):
     b, t, c, h, w = cfg
     g = torch.Generator(device="cuda").manual_seed(0)
     k = torch.randn(b, t, c, h, w, 2, device="cuda", generator=g)
@@ -497,6 +508,20 @@ def test_autograd_fft_and_pointwise(ops, F):
     oo = torch.fft.fftshift(torch.fft.ifft(torch.fft.ifftshift(tt, dim=1), dim=1, norm="ortho"), dim=1) + mu
     g2, = torch.autograd.grad((torch.view_as_real(oo) * w2).sum(), z)
     assert float((g1 - g2).abs().max() / g2.abs().max()) <= 1e-5
+
+
+def test_sparse_upload_of_masked_kspace(ops):
+    """b2s_upload_rows: only sampled rows cross PCIe, the result equals the dense masked k-space bit for bit."""
+    from deep_cine_cardiac_mri_b200 import synth
+    for (b, t, c, h, w) in [(2, 3, 4, 200, 200), (1, 2, 3, 18, 7)]:
+        case = synth.cine_case(77, b, t, c, h, w)
+        host = torch.from_numpy(case["masked_kspace"]).pin_memory()
+        mask = cu(case["mask"])
+        got = ops.upload_masked_kspace(host, mask)
+        torch.cuda.synchronize()
+        assert torch.equal(got.cpu(), host)
+    with pytest.raises(ValueError):
+        ops.upload_masked_kspace(torch.zeros(1, 1, 1, 4, 4, 2), cu(np.ones((1, 1, 1, 4, 1, 1), np.uint8)))
 
 
 def test_dc_step_host_entry():
