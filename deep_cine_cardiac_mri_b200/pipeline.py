@@ -48,6 +48,39 @@ def varnet_hot_path(masked_kspace: torch.Tensor, mask: torch.Tensor,
     return F.complex_abs(ops.sens_reduce(k, sens))
 
 
+_side_streams = {}
+
+
+def varnet_hot_path_streams(masked_kspace: torch.Tensor, mask: torch.Tensor, v=1.0, n_cascades: int = 12, xf: bool = True,
+                            n_streams: int = 2, **kw) -> torch.Tensor:
+    """`varnet_hot_path` with the slice batch split over `n_streams` CUDA streams.
+
+    Slices are independent, and every fused kernel is a persistent grid of one CTA per SM whose last
+    round is ragged (600 images x 2 halves on 148 SMs = 8.1 rounds -> 9): with two streams the tail of one stream's
+    kernel is filled by the head of the other's.  Fork/join is by events only, so the call is CUDA-graph capturable."""
+    b = masked_kspace.shape[0]
+    n = max(1, min(n_streams, b))
+    if n == 1:
+        return varnet_hot_path(masked_kspace, mask, v, n_cascades, xf, **kw)
+    cur = torch.cuda.current_stream()
+    dev = masked_kspace.device
+    pool = _side_streams.setdefault(dev.index, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(dev))
+    bounds = [(i * b) // n for i in range(n + 1)]
+    outs = []
+    for i in range(n):
+        st = pool[i]
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            o = varnet_hot_path(masked_kspace[bounds[i]:bounds[i + 1]], mask[bounds[i]:bounds[i + 1]], v, n_cascades, xf, **kw)
+        o.record_stream(cur)
+        outs.append(o)
+    for i in range(n):
+        cur.wait_stream(pool[i])
+    return torch.cat(outs, 0)
+
+
 def varnet_hot_path_image_domain(masked_kspace: torch.Tensor, mask: torch.Tensor,
                                  v: Union[float, torch.Tensor, Sequence] = 1.0, n_cascades: int = 12, xf: bool = True,
                                  regulariser: Optional[Callable] = None, sens_unet: Optional[Callable] = None,

@@ -231,6 +231,25 @@ def test_whole_hot_path_and_image_domain_variant(ops):
             assert O.ssim(want[i], g[i]) >= 1 - 1e-6
 
 
+def test_hot_path_split_over_streams_and_graph(ops):
+    """Slices split over two streams (fork/join by events) give the single-stream result, eagerly and when the whole
+    call is captured into one CUDA graph (what bench.py replays)."""
+    from deep_cine_cardiac_mri_b200 import pipeline, synth
+    case = synth.cine_case(41, 3, 5, 4, 200, 200)
+    mk, mask = cu(case["masked_kspace"]), cu(case["mask"])
+    v = torch.tensor([0.8], device="cuda")
+    with torch.no_grad():
+        want = pipeline.varnet_hot_path(mk, mask, v, 3)
+        got = pipeline.varnet_hot_path_streams(mk, mask, v, 3, n_streams=2)
+        torch.cuda.synchronize()
+        assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max())
+        g = pipeline.Graphed(lambda: pipeline.varnet_hot_path_streams(mk, mask, v, 3, n_streams=2))
+        for _ in range(2):
+            out = g()
+        torch.cuda.synchronize()
+        assert float((out - want).abs().max()) <= 1e-6 * float(want.abs().max())
+
+
 def test_cinenet_hot_path(ops):
     """pipeline.cinenet_hot_path == oracle chain of conj_grad blocks (cinenet.py:61-73, 136-171, 222-257)."""
     from deep_cine_cardiac_mri_b200 import pipeline, synth
