@@ -348,6 +348,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its banner on stdout; this program prints ONE JSON line
     if args.impl == "reference":
         run_reference(args, rank)
         return
