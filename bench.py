@@ -33,7 +33,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOAD = "XF-VarNet 12-cascade SENSE/DC hot path, 10-coil 15-frame 200x200 cine slices"
-CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=4, streams=2)
+CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=4, streams=2, upload_sms=4)
 METRIC, UNIT = "cine_slices_per_sec", "slices/s"
 
 
@@ -234,7 +234,11 @@ def run_ours(args, rank, world, local):
         assert check <= 1e-5, f"graph replay differs from the eager hot path: {check:.2e}"
 
         # ---- e2e: pinned host buffers in, reconstructed cine out, copies inside the timed region ----
+        #      Only the sampled k-space rows cross PCIe: the masked k-space a scanner pipeline hands over is 75 % zero rows
+        #      (data/transforms.py:66-92), ops.upload_masked_kspace reads the others' neighbours straight from the pinned
+        #      buffer on 4 SMs that the persistent kernels of the captured step leave free (b2s_set_sm_reserve).
         copy_stream, comp_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        ops.set_sm_reserve(CFG["upload_sms"])
 
         def e2e_fn(k_in, m_in):
             return pipeline.varnet_hot_path_streams(k_in, m_in, v, CFG["cascades"], xf=True, n_streams=NS)
@@ -250,8 +254,8 @@ def run_ours(args, rank, world, local):
                 s = i % 2
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(freed[s])
-                    graphs[s].inputs[0].copy_(mk_host, non_blocking=True)
                     graphs[s].inputs[1].copy_(mask_host, non_blocking=True)
+                    ops.upload_masked_kspace(mk_host, graphs[s].inputs[1], out=graphs[s].inputs[0])
                     ready[s].record(copy_stream)
                 with torch.cuda.stream(comp_stream):
                     comp_stream.wait_event(ready[s])
@@ -270,7 +274,11 @@ def run_ours(args, rank, world, local):
         torch.cuda.synchronize()
         e2e_sec = bdist.max_over_ranks(time.perf_counter() - t0, dev)
         bdist.barrier()
+        check = float((out_host[(K - 1) % 2].to(dev) - out).abs().max() / out.abs().max())
+        assert check <= 1e-5, f"end-to-end result differs from the device-resident run: {check:.2e}"
         del graphs
+        ops.set_sm_reserve(0)
+        h2d_bytes = int(mask_np.astype("int64").sum()) * c * w * 8 + mask_host.numel()
 
         # ---- same function, image-domain formulation (k-space never materialised), reported as an extra
         for _ in range(2):
@@ -328,7 +336,9 @@ def run_ours(args, rank, world, local):
                    "l2": f"inputs larger than L2: {alg['K'] / 1e6:.0f} MB k-space per tensor per step", "regulariser": "identity (outside the hot path)",
                    "launch": f"whole step captured in one CUDA graph, slices split over {CFG['streams']} streams inside it"},
         "clocks": clocks,
-        "e2e": {"value": world * nb * K / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(mk_host.numel() * 4 + mask_host.numel()),
+        "e2e": {"value": world * nb * K / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "h2d": f"sampled k-space rows only ({h2d_bytes / 1e6:.0f} of {mk_host.numel() * 4 / 1e6:.0f} MB dense), read from pinned memory by "
+                       f"{CFG['upload_sms']} SMs reserved for the upload",
                 "d2h_bytes_per_step": int(b * t * h * w * 4)},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -22,6 +22,7 @@ SIGNATURES = {
     "b2s_version": [],
     "b2s_last_error": [],
     "b2s_launch_count": [_i],
+    "b2s_set_sm_reserve": [_i],
     "b2s_debug_strip_status": [],
     "b2s_set_fused_path": [_i],
     "b2s_has_fused_plan": [_i, _i],

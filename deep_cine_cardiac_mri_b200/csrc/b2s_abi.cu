@@ -5,6 +5,7 @@
 namespace b2s {
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_kernel_launches{0};
+std::atomic<int> g_sm_reserve{0};
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -15,6 +16,11 @@ void set_error(const char* fmt, ...) {
 
 extern "C" int b2s_version(void) { return 100; }
 extern "C" const char* b2s_last_error(void) { return b2s::g_err; }
+extern "C" int b2s_set_sm_reserve(int n_sms) {
+  if (n_sms < 0 || n_sms > 64) { b2s::set_error("b2s_set_sm_reserve: 0 <= n_sms <= 64"); return B2S_EINVAL; }
+  b2s::g_sm_reserve.store(n_sms);
+  return B2S_OK;
+}
 extern "C" unsigned long long b2s_launch_count(int reset) {
   return reset ? b2s::g_kernel_launches.exchange(0) : b2s::g_kernel_launches.load();
 }

@@ -13,7 +13,8 @@ void set_error(const char* fmt, ...);          // defined in b2s_abi.cu (thread-
 
 inline int fail(int code, const char* what) { set_error("%s", what); return code; }
 
-extern std::atomic<unsigned long long> g_kernel_launches;   // b2s_abi.cu; kernels launched through this library
+extern std::atomic<unsigned long long> g_kernel_launches;
+extern std::atomic<int> g_sm_reserve;          // b2s_abi.cu; SMs the persistent kernels leave free (b2s_set_sm_reserve)   // b2s_abi.cu; kernels launched through this library
 
 inline int check_launch(const char* what, int n_kernels = 1) {
   g_kernel_launches.fetch_add((unsigned long long)n_kernels, std::memory_order_relaxed);

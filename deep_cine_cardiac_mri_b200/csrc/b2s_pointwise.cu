@@ -456,11 +456,15 @@ extern "C" int b2s_upload_rows(const float* kspace_host, const uint8_t* mask, fl
   }
   const float* src = (const float*)attr.devicePointer;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = 148 * 8;
+  // With SMs reserved (b2s_set_sm_reserve) the upload runs as that many 1024-thread CTAs on exactly those SMs, beside
+  // the persistent compute kernels of another stream; otherwise it spreads over the whole GPU.
+  const int reserve = g_sm_reserve.load();
+  const unsigned grid = reserve > 0 ? (unsigned)reserve : 148u * 8u;
+  const unsigned nt = reserve > 0 ? 1024u : (unsigned)NT;
   if (w % 2 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)kspace_dev % 16 == 0))
-    upload_rows_kernel<float4><<<grid, NT, 0, st>>>((const float4*)src, mask, (float4*)kspace_dev, c, h, w / 2, n_rows);
+    upload_rows_kernel<float4><<<grid, nt, 0, st>>>((const float4*)src, mask, (float4*)kspace_dev, c, h, w / 2, n_rows);
   else
-    upload_rows_kernel<float2><<<grid, NT, 0, st>>>((const float2*)src, mask, (float2*)kspace_dev, c, h, w, n_rows);
+    upload_rows_kernel<float2><<<grid, nt, 0, st>>>((const float2*)src, mask, (float2*)kspace_dev, c, h, w, n_rows);
   return check_launch("upload_rows_kernel");
 }
 

@@ -100,6 +100,12 @@ def set_fused_path(path) -> None:
     _lib.check(_lib.lib().b2s_set_fused_path(code), "set_fused_path")
 
 
+def set_sm_reserve(n_sms: int) -> None:
+    """Keep `n_sms` SMs out of the persistent fused kernels' grids; `upload_masked_kspace` then runs on exactly those
+    (see include/b200sense.h: b2s_set_sm_reserve).  Affects launches (and graph captures) made afterwards."""
+    _lib.check(_lib.lib().b2s_set_sm_reserve(int(n_sms)), "set_sm_reserve")
+
+
 def strip_status() -> int:
     """0 when no inter-CTA dependency wait of the strip kernels ever timed out on the current device (synchronises)."""
     return int(_lib.lib().b2s_debug_strip_status())

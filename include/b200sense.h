@@ -56,6 +56,10 @@ int b2s_version(void);
 const char* b2s_last_error(void);
 /* number of CUDA kernels this library has launched so far (host-side counter; reset != 0 zeroes it) */
 unsigned long long b2s_launch_count(int reset);
+/* Leave `n_sms` SMs free: the persistent fused kernels (one CTA per SM) launch that many CTAs fewer, and
+ * b2s_upload_rows runs as `n_sms` 1024-thread CTAs on them - the sparse upload of the next batch then overlaps the
+ * compute of the current one instead of queueing behind its statically strided grids.  0 (default) = use every SM. */
+int b2s_set_sm_reserve(int n_sms);
 /* Diagnostic of the strip-streamed kernels (csrc/strip_core.cuh): synchronises the current device and returns 0 when
  * no inter-CTA dependency wait ever timed out on it (non-zero = results of that launch are invalid; -1 = CUDA error). */
 int b2s_debug_strip_status(void);

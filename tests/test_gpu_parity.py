@@ -536,9 +536,14 @@ def test_sparse_upload_of_masked_kspace(ops):
         case = synth.cine_case(77, b, t, c, h, w)
         host = torch.from_numpy(case["masked_kspace"]).pin_memory()
         mask = cu(case["mask"])
-        got = ops.upload_masked_kspace(host, mask)
-        torch.cuda.synchronize()
-        assert torch.equal(got.cpu(), host)
+        for reserve in (0, 4):                 # whole-GPU grid, and 4 x 1024 threads on SMs kept out of the persistent grids
+            ops.set_sm_reserve(reserve)
+            got = ops.upload_masked_kspace(host, mask)
+            k2 = ops.sens_reduce(got, cu(case["sens"]))            # a persistent kernel with the reduced grid
+            torch.cuda.synchronize()
+            assert torch.equal(got.cpu(), host)
+            assert rel(k2, O.sens_reduce(f64(case["masked_kspace"]), f64(case["sens"]), keepdim=False)) <= TOL
+        ops.set_sm_reserve(0)
     with pytest.raises(ValueError):
         ops.upload_masked_kspace(torch.zeros(1, 1, 1, 4, 4, 2), cu(np.ones((1, 1, 1, 4, 1, 1), np.uint8)))
 
