@@ -34,6 +34,8 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOAD = "XF-VarNet 12-cascade SENSE/DC hot path, 10-coil 15-frame 200x200 cine slices"
 CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=4, streams=2, upload_sms=4)
+if os.environ.get("B2S_BENCH_UPLOAD_SMS"):          # dev override
+    CFG["upload_sms"] = int(os.environ["B2S_BENCH_UPLOAD_SMS"])
 METRIC, UNIT = "cine_slices_per_sec", "slices/s"
 
 

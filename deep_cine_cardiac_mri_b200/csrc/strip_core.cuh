@@ -1,33 +1,37 @@
 // Strip-streamed fused centred 2-D FFT ("two passes through L2, one pass through HBM").
 //
-// The half-split kernel (fft2_core.cuh) keeps one image per SM on chip and is bound by the L2 -> SM
-// ingest of a single resident CTA.  This kernel gives up on-chip residency of the *image* and keeps only
-// the *intermediate* on chip - in the 126 MB L2 instead of shared memory:
+// The half-split kernel (fft2_core.cuh) keeps one image per SM on chip and is bound by what a single resident
+// CTA can ingest from L2.  This kernel gives up on-chip residency of the *image* and keeps only the *intermediate*
+// on chip - in the 126 MB L2 instead of shared memory:
 //
-//   pass R  unit = NV consecutive rows of one image (NV*W*8 contiguous bytes).  W-point transform per
-//           row in two register steps (W = N1*N2: N1-point codelet over stride-N2 elements, twiddle,
-//           exchange through shared memory, N2-point codelet).  The prologue functor supplies the
-//           element (identity | S_c * x_t | row-weighted k-space); results go to a scratch ring in
-//           global memory whose layout is strip-major, so pass C reads contiguous blocks.
-//   pass C  unit = a strip of NV columns of one image.  H-point transform per column, same two steps;
-//           the epilogue functor consumes the result (store | mask / soft-DC blend / residual |
-//           conj(S)-multiply + coil sum).
+//   pass R  sub-unit = 4 consecutive rows of one image (4*W*8 contiguous bytes).  W-point transform per row in two
+//           steps (W = N1*N2): N1-point register codelet over stride-N2 elements, twiddle (table also carries the
+//           centring signs and the scale), exchange through the warp's private shared-memory buffer, then the N2 =
+//           A*B points of one (row, k1) belong to ONE lane which runs A-point codelets, constant twiddles and
+//           B-point codelets in place.  The prologue functor supplies the element (identity | S_c * x_t |
+//           row-weighted k-space); results go to a scratch ring in global memory whose layout is strip-major, so
+//           pass C reads contiguous blocks.
+//   pass C  sub-unit = a strip of 4 columns of one image.  H-point transform per column, same two steps; the epilogue
+//           functor consumes the result (store | mask / soft-DC blend / residual | conj(S)-multiply + coil sum).
 //
-// One persistent kernel runs both passes: CTAs draw units from an atomic ticket counter; the ticket
-// order interleaves pass-R units of image p with pass-C units of image p - LAG, so the scratch ring
-// (NSLOT images, 64 x 320 KB = 20 MB at 200 x 200) is written and re-read while still L2-resident and the
-// k-space crosses HBM once per direction.  Dependencies are per-image counters (release/acquire):
-// pass C of image i waits for its H/NV pass-R units; pass R of image i waits until pass C of image
-// i - NSLOT (the previous owner of the ring slot) is finished.  Tickets are handed out in order and a
-// unit only ever waits for units with smaller tickets, i.e. units that are already running: no deadlock.
-//
-// Units are small (64 or 128 threads, ~17 KB of shared memory), so 8 CTAs are resident per SM and
-// their load / compute / store phases overlap without any explicit software pipeline.
+// One persistent kernel runs both passes.  WARPS are the unit of execution: after the table build there is no CTA
+// barrier; each warp draws tickets (one sub-unit each) from an atomic counter, issues the global loads of its next
+// sub-unit into registers before it runs the second step of the current one, and signals completion with
+// red.release.  The ticket order puts pass C of image p - LAG behind pass R of image p, so the scratch ring (NSLOT
+// images, 80 x 320 KB = 26 MB at 200 x 200) is written and re-read while still L2-resident and the k-space crosses HBM
+// once per direction.  Dependencies are per-image counters (release/acquire): pass C of image i waits for its H/4
+// pass-R sub-units; pass R of image i waits until pass C of image i - NSLOT (the previous owner of the ring slot) is
+// finished.  Tickets are handed out in order and a sub-unit only ever waits for smaller tickets, i.e. for sub-units
+// that are already running: no deadlock; waits are bounded and flag `status` instead of hanging the GPU.
 //
 // Centring (utils/fftc.py:59-110) for even sizes: fftc(x)[k] = (-1)^(N/2) (-1)^k DFT((-1)^n x[n])[k].
 // With n = N2*n1 + n2 and k = k1 + N1*k2 (N1 even): (-1)^n1 (N2 odd) is a rotation of the N1-point
 // codelet's outputs by N1/2, (-1)^(n2 + k1) goes into the twiddle table, which also carries the scale.
 // The inverse transform runs the forward machinery on re/im-swapped data.
+//
+// Measured on B200 (profiles/r1_strip_experiment.md): the memory side works (DRAM traffic = algorithmic bytes), but
+// the formulation spends 20-60 % more instructions than the on-chip kernels and loses to them; it is selectable
+// (b2s_set_fused_path / B2S_PATH=strip) and covered by the same parity tests, not the default.
 #pragma once
 #include <stdint.h>
 #include "codelets.cuh"
