@@ -37,6 +37,7 @@ CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=4, streams
 if os.environ.get("B2S_BENCH_UPLOAD_SMS"):          # dev override
     CFG["upload_sms"] = int(os.environ["B2S_BENCH_UPLOAD_SMS"])
 METRIC, UNIT = "cine_slices_per_sec", "slices/s"
+_OUT = sys.stdout
 
 
 # --------------------------------------------------------------------------- #
@@ -149,7 +150,7 @@ def run_reference(args, rank):
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------- #
@@ -356,7 +357,7 @@ def run_ours(args, rank, world, local):
                                  "note": "identical outputs; each cascade = one on-chip normal-operator launch "
                                          "(A^H DC A x = ssq x - eta (A^H M A x - A^H ref)); not the headline"},
     }
-    print(json.dumps(result), flush=True)
+    print(json.dumps(result), file=_OUT, flush=True)
 
 
 def main():
@@ -369,8 +370,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its banner on stdout; this program prints ONE JSON line
+    # This program prints ONE JSON line on stdout.  Libraries write there too (NCCL's version banner at communicator
+    # creation), so file descriptor 1 is pointed at stderr for the duration and the line goes to the saved descriptor.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
