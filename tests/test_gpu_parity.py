@@ -350,6 +350,32 @@ def test_block_dropins_with_identity_regularisers(ops):
     for _ in range(2):
         kk = O.varnet_block(kk, mk, d["mask"], d["sens"], v)
     assert rel(out, O.complex_abs(O.sens_reduce(kk, d["sens"], keepdim=False))) <= 2e-5
+    # ... and the inference fast path of the same drop-in: cascades that look like VarNetBlocks (lambda_reg, dynamic_type)
+    # run in the image domain under no_grad (one normal-operator launch each), same result
+    def mk_block(dyn, model):
+        bb = types.SimpleNamespace(dynamic_type=dyn, weight_sharing=False, model=model, Softplus=torch.nn.Softplus(1.), lambda_reg=lam)
+        bb.xfyf_transform = types.MethodType(blocks.varnet_xfyf_transform, bb)
+        return bb
+    class Blk(torch.nn.Module):
+        def __init__(self, dyn, model):
+            super().__init__()
+            self.dynamic_type, self.weight_sharing, self.model = dyn, False, model
+            self.Softplus, self.lambda_reg = torch.nn.Softplus(1.), torch.nn.Parameter(lam.clone())
+            self.xfyf_transform = types.MethodType(blocks.varnet_xfyf_transform, self)
+        def forward(self, kk, rk, mm, ss):
+            return blocks.varnet_block_forward(self, kk, rk, mm, ss)
+    net2 = types.SimpleNamespace(sens_net=lambda kk, mm: sens, cascades=[Blk("2D", ident), Blk("XF", torch.nn.ModuleList([ident, ident]))])
+    want2 = O.complex_abs(O.sens_reduce(kk, d["sens"], keepdim=False))
+    with torch.no_grad():
+        fast = blocks.varnet_forward(net2, cu(mk.astype(np.float32)), mask)
+    slow = blocks.varnet_forward(net2, cu(mk.astype(np.float32)), mask)            # autograd on: k-space path
+    assert rel(fast, want2) <= 2e-5 and rel(slow, want2) <= 2e-5
+    assert float((fast - slow.detach()).abs().max()) <= 1e-5 * float(slow.abs().max())
+    blocks.set_image_domain_inference(False)
+    with torch.no_grad():
+        again = blocks.varnet_forward(net2, cu(mk.astype(np.float32)), mask)       # k-space path (coil sums by atomics: ~1 ulp)
+        assert float((again - slow.detach()).abs().max()) <= 1e-6 * float(slow.abs().max())
+    blocks.set_image_domain_inference(True)
     cine = types.SimpleNamespace(cascades=[lambda ip, ir, mm, ss: ip + ir])
     out = blocks.cinenet_forward(cine, cu(mk.astype(np.float32)), mask, sens)
     assert rel(out, O.complex_abs(2 * O.sens_reduce(mk, d["sens"], keepdim=False))) <= TOL
