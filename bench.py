@@ -34,8 +34,9 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOAD = "XF-VarNet 12-cascade SENSE/DC hot path, 10-coil 15-frame 200x200 cine slices"
 CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=4, streams=2, upload_sms=4)
-if os.environ.get("B2S_BENCH_UPLOAD_SMS"):          # dev override
-    CFG["upload_sms"] = int(os.environ["B2S_BENCH_UPLOAD_SMS"])
+for _k, _e in (("upload_sms", "B2S_BENCH_UPLOAD_SMS"), ("streams", "B2S_BENCH_STREAMS"), ("slices_per_gpu_step", "B2S_BENCH_SLICES")):
+    if os.environ.get(_e):                          # dev overrides
+        CFG[_k] = int(os.environ[_e])
 METRIC, UNIT = "cine_slices_per_sec", "slices/s"
 _OUT = sys.stdout
 
