@@ -150,7 +150,8 @@ template <class P, class Pro> struct PhaseA {
   static constexpr int STEPS = TPT * R;
   static constexpr int NK = D::NKEEP;
   static constexpr int QD = Pro::template qdepth<R, false, NC>();   // steps in flight
-  static_assert(STEPS % QD == 0 && (2 * R) % QD == 0 && TPT % 2 == 0, "queue depth must divide two tasks' steps");
+  static constexpr int TT = ((2 * R) % QD == 0) ? 2 : 4;            // tasks per loop trip (queue slots stay compile-time)
+  static_assert(STEPS % QD == 0 && (TT * R) % QD == 0 && TPT % TT == 0, "queue depth must divide one trip's steps");
   typedef typename Pro::template Unit<NC> Unit;
   struct Queue { Unit u[QD]; };
 
@@ -179,9 +180,9 @@ template <class P, class Pro> struct PhaseA {
     const float h = 0.70710678118654752440f;
     float ur[NC][NK][R], ui[NC][NK][R];     // [column][m-block r][column-group index i]
 #pragma unroll 1
-    for (int kp = 0; kp < TPT; kp += 2)     // two tasks per trip: queue slots stay compile-time, code stays small
+    for (int kp = 0; kp < TPT; kp += TT)    // TT tasks per trip: queue slots stay compile-time, code stays small
 #pragma unroll
-    for (int u = 0; u < 2 * R; ++u) {
+    for (int u = 0; u < TT * R; ++u) {
       const int s = kp * R + u;
       const int k = kp + u / R, i = u % R, slot = u % QD;
       int g, x0;
