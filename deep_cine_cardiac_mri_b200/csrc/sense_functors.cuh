@@ -132,10 +132,11 @@ template <int H, int W> struct ProExpand {
     const long long c = image % C, bt = image / C, b = bt / T;
     Ctx k; k.a = img + bt * hw; k.s = sens + (b * C + c) * hw; return k;
   }
-  // steps of raw loads in flight per thread (one step = 8 rows x {x, S} = 32 registers per column).  Deeper is better
-  // until the queue spills: 200 x 200 (R = 5): 4 steps with 64-bit loads (a loop trip of 4 tasks keeps the slots
-  // compile-time), 1 with 128-bit loads; 256 x 256 (R = 8): 2 either way.
-  template <int R, bool PAIRED = false, int NC = 1> static constexpr int qdepth() { return PAIRED ? 1 : (R == 5 ? (NC > 1 ? 1 : 4) : 2); }   // x 16 loads in flight per thread
+  // steps of raw loads in flight per thread (one step = 8 rows x {x, S} = 32 registers per column): 2 with 64-bit loads;
+  // with 128-bit loads 1 at 200 x 200 (R = 5; 2 spill) and 2 at 256 x 256 (R = 8).  A 4-step queue at 200 x 200 (loop
+  // trip of 4 tasks, PhaseA::TT) wins operator microbenchmarks on random data (187 -> 181 us) but loses inside the
+  // 12-cascade pipeline on cine data (184.8 -> 188.8 us per launch, profiles/r1_analysis.md), so it is not used.
+  template <int R, bool PAIRED = false, int NC = 1> static constexpr int qdepth() { return PAIRED ? 1 : (NC > 1 ? (R == 5 ? 1 : 2) : 2); }   // x 16 loads in flight per thread
   template <int NC> struct Unit { cvec<NC> a[8], s[8]; };
   template <int NC, int RS> B2S_HD void fetch(const Ctx& c, int, int off, Unit<NC>& u) const {
     const cfloat* pa = c.a + off; const cfloat* ps = c.s + off;
@@ -241,9 +242,9 @@ template <int H, int W, int MODE> struct EpiKspace {
     if (MODE >= 2) {
 #pragma unroll
       for (int k = 0; k < G; ++k) {                        // DC needs ref on sampled rows only
-        if (MODE == 2) {                                   // defined on every path: a write under a predicate alone would keep the
-#pragma unroll                                             // previous task's 2*G*NC registers alive across the whole persistent loop
-          for (int n = 0; n < NC; ++n) pre.r[k].v[n] = make_c(0.f, 0.f);
+        if (MODE == 2 && H == 256) {                       // defined on every path: a write under a predicate alone keeps the previous
+#pragma unroll                                             // task's 2*G*NC registers alive across the whole persistent loop (measured: helps
+          for (int n = 0; n < NC; ++n) pre.r[k].v[n] = make_c(0.f, 0.f);   // the 256 x 256 plan, costs 4 us at 200 x 200)
         }
         if (MODE == 3 || ((pre.mbits >> k) & 1u)) pre.r[k] = ldv_stream<NC>(t.r + 8 * k * W);
       }

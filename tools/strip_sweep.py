@@ -16,6 +16,8 @@ m = (torch.rand(b, t, h, device=dev, generator=g) < 0.25).to(torch.uint8)
 v = torch.tensor([1.0], device=dev)
 i = [0]
 def nxt(): i[0] = (i[0] + 1) % 3; return i[0]
+import os
+warm = bool(os.environ.get("B2S_SWEEP_WARM"))       # the cascade's reference k-space is the same tensor every time
 r = [timeit(lambda: ops.raw_fft2c(ks[nxt()], False, 1)), timeit(lambda: ops.raw_sens_reduce(ks[nxt()], s)),
-     timeit(lambda: ops.raw_sens_expand(x, s, 2, ks[nxt()], m, v))]
+     timeit(lambda: ops.raw_sens_expand(x, s, 2, ks[0] if warm else ks[nxt()], m, v))]
 print("fft2c %.1f us  sens_reduce %.1f us  sens_expand_dc %.1f us" % tuple(1e6 * q for q in r))
