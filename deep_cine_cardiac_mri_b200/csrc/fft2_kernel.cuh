@@ -23,7 +23,8 @@ __device__ unsigned long long g_phase_cycles[8];
 // prefetch use it).
 template <class P, class Pro, class Epi, bool CARRY>
 __global__ void __launch_bounds__(P::NT, P::CTAS)
-fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_items, const unsigned stagger_ns) {
+fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_items, const unsigned stagger_ns,
+                 const int reverse) {
   using D = Derived<P>;
   extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
   cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);
@@ -46,23 +47,29 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
 #endif
   typedef PhaseA<P, Pro> PA;
   typename PA::Queue queue;
-  if (CARRY && (int)blockIdx.x < n_items) PA::prefill(pro, pro.ctx(blockIdx.x / P::FOLD), tid, queue);
+  // reverse != 0: walk the images from the last to the first.  A kernel that consumes what the previous kernel just
+  // streamed out (sens_reduce after sens_expand + DC: 192 MB through a 126 MB L2) then starts with the part that is
+  // still cached instead of the part that was evicted first.
+  const int n_img = n_items / P::FOLD;
+  auto image_of = [&](int item) -> long long { const int n = item / P::FOLD; return reverse ? n_img - 1 - n : n; };
+  if (CARRY && (int)blockIdx.x < n_items) PA::prefill(pro, pro.ctx(image_of(blockIdx.x)), tid, queue);
 
 #pragma unroll 1
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const long long image = item / P::FOLD;
+    const long long image = image_of(item);
     const int q = item % P::FOLD;
     const int next = item + (int)gridDim.x;
     const bool has_next = next < n_items;
+    const long long next_image = has_next ? image_of(next) : image;
     if (!CARRY) PA::prefill(pro, pro.ctx(image), tid, queue);
     // run<true>: the barrier that protects B (and the mask rows) from the previous item's Phase C sits
     // inside, just before the first write into B, so the first loads of this item are already in flight
-    PA::template run<true>(pro, pro.ctx(image), pro.ctx(has_next ? (next / P::FOLD) : image), CARRY && has_next, smem, q, tid, queue);
+    PA::template run<true>(pro, pro.ctx(image), pro.ctx(next_image), CARRY && has_next, smem, q, tid, queue);
     __syncthreads();
     epi.stage_mask(image, mrow, tid, P::NT);               // visible to Phase C through the barriers below
     B2S_TICK(0);
     // warm L2 with the rest of the next item while this SM is busy with register codelets (Phases B, C)
-    if (has_next && (next % P::FOLD) == 0) pro.l2_prefetch(next / P::FOLD, tid);
+    if (has_next && (next % P::FOLD) == 0) pro.l2_prefetch(next_image, tid);
     epi.l2_prefetch(image, q, P::FOLD, tid);                        // what Phase C will read (issued here, not before
                                                            // Phase A: bulk prefetches compete with its demand loads)
 
