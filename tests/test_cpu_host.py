@@ -44,6 +44,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.b2s_scratch_bytes(1, 2, 3, 8, 6) == 2 * 3 * 8 * 6 * 8
 
 
+def test_abi_option_entry_points_validate_their_arguments():
+    """b2s_set_fused_path / b2s_set_sm_reserve are host-only switches: callable without a GPU, bad values are refused."""
+    from deep_cine_cardiac_mri_b200 import _lib, ops
+    lib = _lib.lib()
+    assert lib.b2s_set_fused_path(2) == 1 and b"b2s_set_fused_path" in lib.b2s_last_error()
+    assert lib.b2s_set_fused_path(1) == 0 and lib.b2s_set_fused_path(0) == 0 and lib.b2s_set_fused_path(-1) == 0
+    assert lib.b2s_set_sm_reserve(-1) == 1 and lib.b2s_set_sm_reserve(65) == 1
+    assert lib.b2s_set_sm_reserve(4) == 0 and lib.b2s_set_sm_reserve(0) == 0
+    with pytest.raises(KeyError):
+        ops.set_fused_path("tensor-cores")
+    ops.set_fused_path("strip"); ops.set_fused_path(None)
+    with pytest.raises(ValueError):
+        ops.upload_masked_kspace(__import__("torch").zeros(1, 1, 1, 4, 4, 2), __import__("torch").zeros(1, 1, 4, dtype=__import__("torch").uint8))
+
+
 def test_abi_rejects_bad_arguments_without_a_gpu():
     from deep_cine_cardiac_mri_b200 import _lib
     lib = _lib.lib()
