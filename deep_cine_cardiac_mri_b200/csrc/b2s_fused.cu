@@ -31,18 +31,13 @@ static int use_quarter() {
   return q;
 }
 
-// B2S_REVERSE: 1 (default) = sens_reduce walks the images last-to-first (it usually follows the kernel that wrote them)
-static int use_reverse() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("B2S_REVERSE"); v = e ? atoi(e) : 1; }
-  return v;
-}
-
-template <class P, class Pro, class Epi, bool CARRY = false>
-int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st, int reverse = 0) {
+// REVERSE: the kernel walks the images last-to-first (sens_reduce: it usually follows the kernel that wrote them, and
+// the end of a 192 MB stream is what is still in the 126 MB L2)
+template <class P, class Pro, class Epi, bool CARRY = false, bool REVERSE = false>
+int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st) {
   if (n_images <= 0) return B2S_OK;
   if (P::FOLD * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
-  auto kern = fft2_half_kernel<P, Pro, Epi, CARRY>;
+  auto kern = fft2_half_kernel<P, Pro, Epi, CARRY, REVERSE>;
   int dev = 0, sms = 0;
   B2S_CUDA(cudaGetDevice(&dev));
   static std::atomic<int> sm_count[64];       // immutable per-device facts (zero-initialised statics)
@@ -59,7 +54,7 @@ int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, 
   const unsigned grid = (unsigned)(n_items < slots ? n_items : slots);   // persistent: P::CTAS CTAs per SM
   static int stagger = -1;
   if (stagger < 0) { const char* e = getenv("B2S_STAGGER_NS"); stagger = e ? atoi(e) : 0; }
-  kern<<<grid, P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale, n_items, (unsigned)stagger, reverse);
+  kern<<<grid, P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale, n_items, (unsigned)stagger);
   return check_launch("fft2_half_kernel");
 }
 
@@ -152,7 +147,7 @@ int plan_reduce(const float* kspace, const float* mult, float* out, const uint8_
   {                                                                     \
     ProKspace<H, W, M> pro{(const cfloat*)kspace, mask, v, c, hw};      \
     if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
-    return launch_fused<P>(pro, epi, s, n, st, use_reverse());          \
+    return launch_fused<P, ProKspace<H, W, M>, EpiReduce<H, W>, false, true>(pro, epi, s, n, st); \
   }
   switch (weight_mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) default: B2S_RUN(2) }
 #undef B2S_RUN

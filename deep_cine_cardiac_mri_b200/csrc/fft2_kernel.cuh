@@ -21,10 +21,9 @@ __device__ unsigned long long g_phase_cycles[8];
 // CARRY: keep the Phase A load queue alive across Phases B/C and the item boundary (hides the head
 // latency of every Phase A; costs QD*16 registers during Phase C, so only epilogues without operand
 // prefetch use it).
-template <class P, class Pro, class Epi, bool CARRY>
+template <class P, class Pro, class Epi, bool CARRY, bool REVERSE = false>
 __global__ void __launch_bounds__(P::NT, P::CTAS)
-fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_items, const unsigned stagger_ns,
-                 const int reverse) {
+fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_items, const unsigned stagger_ns) {
   using D = Derived<P>;
   extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
   cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);
@@ -47,11 +46,12 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
 #endif
   typedef PhaseA<P, Pro> PA;
   typename PA::Queue queue;
-  // reverse != 0: walk the images from the last to the first.  A kernel that consumes what the previous kernel just
+  // REVERSE: walk the images from the last to the first (a template parameter: as a run-time argument it cost the
+  // forward kernels 2 % through register allocation).  A kernel that consumes what the previous kernel just
   // streamed out (sens_reduce after sens_expand + DC: 192 MB through a 126 MB L2) then starts with the part that is
   // still cached instead of the part that was evicted first.
   const int n_img = n_items / P::FOLD;
-  auto image_of = [&](int item) -> long long { const int n = item / P::FOLD; return reverse ? n_img - 1 - n : n; };
+  auto image_of = [&](int item) -> long long { const int n = item / P::FOLD; return REVERSE ? n_img - 1 - n : n; };
   if (CARRY && (int)blockIdx.x < n_items) PA::prefill(pro, pro.ctx(image_of(blockIdx.x)), tid, queue);
 
 #pragma unroll 1
