@@ -52,9 +52,7 @@ int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, 
   const int n_items = (int)(P::FOLD * n_images);
   const int slots = (sms - g_sm_reserve.load() > 0 ? sms - g_sm_reserve.load() : 1) * P::CTAS;   // see b2s_set_sm_reserve
   const unsigned grid = (unsigned)(n_items < slots ? n_items : slots);   // persistent: P::CTAS CTAs per SM
-  static int stagger = -1;
-  if (stagger < 0) { const char* e = getenv("B2S_STAGGER_NS"); stagger = e ? atoi(e) : 0; }
-  kern<<<grid, P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale, n_items, (unsigned)stagger);
+  kern<<<grid, P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale, n_items);
   return check_launch("fft2_half_kernel");
 }
 

@@ -23,7 +23,7 @@ __device__ unsigned long long g_phase_cycles[8];
 // prefetch use it).
 template <class P, class Pro, class Epi, bool CARRY, bool REVERSE = false>
 __global__ void __launch_bounds__(P::NT, P::CTAS)
-fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_items, const unsigned stagger_ns) {
+fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_items) {
   using D = Derived<P>;
   extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
   cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);
@@ -31,14 +31,6 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
   const int tid = threadIdx.x;
 
   build_tables<P>(smem, tid, P::NT);
-  if (stagger_ns && tid == 0) {
-    // de-phase the persistent CTAs: identical work items would otherwise keep every SM in the
-    // same (load | compute | store) phase at the same time and serialise HBM against the math
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    const unsigned long long wait = (unsigned long long)(blockIdx.x & 3u) * stagger_ns;
-    do { __nanosleep(256); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < wait);
-  }
   __syncthreads();
 
 #ifdef B2S_PHASE_TIMING
