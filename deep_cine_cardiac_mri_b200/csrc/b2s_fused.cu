@@ -4,6 +4,7 @@
 #include "b2s_common.cuh"
 #include "sense_functors.cuh"
 #include "fft2_kernel.cuh"
+#include "fft2_whole.cuh"
 
 using namespace b2s;
 
@@ -14,7 +15,9 @@ typedef Plan<200, 200, 128, 1, 4> P200Q;   // quarter split: 2 CTAs x 4 warps pe
 typedef Plan<256, 256, 256, 1, 4> P256;    // quarter split, 1 CTA/SM
 typedef Plan<200, 200, 256, 2, 2, 1> P200W; // half split, 128-bit Phase A loads (two columns per thread)
 typedef Plan<256, 256, 256, 2, 4, 1> P256W; // quarter split, 128-bit Phase A loads
-constexpr int W256_PLAIN = 0;               // auto choice of P256W for fft2c / sens_reduce (sens_expand: always)
+constexpr int W256_PLAIN = 0;
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static int use_whole() { return env_int("B2S_WHOLE", 1); }   // 200 x 200: whole-image kernel with the TMEM parking lot               // auto choice of P256W for fft2c / sens_reduce (sens_expand: always)
 
 // B2S_WIDE: unset/-1 = auto (128-bit Phase A only where it measured faster: the two-stream sens_expand
 // without the DC epilogue, 148 vs 162 us), 0 = never, 1 = always.
@@ -34,8 +37,8 @@ static int use_quarter() {
 // REVERSE: the kernel walks the images last-to-first (sens_reduce: it usually follows the kernel that wrote them, and
 // the end of a 192 MB stream is what is still in the 126 MB L2)
 template <class P, class Pro, class Epi, bool CARRY = false, bool REVERSE = false>
-int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st) {
-  if (n_images <= 0) return B2S_OK;
+int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st, int64_t first_image = 0) {
+  if (n_images <= first_image) return B2S_OK;
   if (P::FOLD * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
   auto kern = fft2_half_kernel<P, Pro, Epi, CARRY, REVERSE>;
   int dev = 0, sms = 0;
@@ -49,11 +52,41 @@ int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, 
     B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<P>::SMEM_BYTES));
     configured[dev].store(true);
   }
-  const int n_items = (int)(P::FOLD * n_images);
+  const int n_items = (int)(P::FOLD * n_images), item0 = (int)(P::FOLD * first_image);   // (reverse order: the LAST first_image images are skipped)
   const int slots = (sms - g_sm_reserve.load() > 0 ? sms - g_sm_reserve.load() : 1) * P::CTAS;   // see b2s_set_sm_reserve
-  const unsigned grid = (unsigned)(n_items < slots ? n_items : slots);   // persistent: P::CTAS CTAs per SM
-  kern<<<grid, P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale, n_items);
+  const unsigned grid = (unsigned)(n_items - item0 < slots ? n_items - item0 : slots);   // persistent: P::CTAS CTAs per SM
+  kern<<<grid, P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale, n_items, item0);
   return check_launch("fft2_half_kernel");
+}
+
+// Whole-image kernel (fft2_whole.cuh, TMEM parking lot) on as many images as fill whole rounds of the persistent
+// grid; a remainder that fits one round of half items (2 * rem <= CTAs) goes through the half-split kernel behind it
+// (a ragged last round of whole images would idle most SMs for a full image time).
+template <class P, class Pro, class Epi, int QD, int TT, bool CARRY = false, bool REVERSE = false>
+int launch_whole(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st) {
+  if (n_images <= 0) return B2S_OK;
+  if (2 * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
+  auto kern = fft2_whole_kernel<P, Pro, Epi, QD, TT, CARRY, REVERSE>;
+  int dev = 0;
+  B2S_CUDA(cudaGetDevice(&dev));
+  static std::atomic<int> sm_count[64];
+  static std::atomic<bool> configured[64];
+  if (dev < 0 || dev >= 64) return fail(B2S_EUNSUPPORTED, "device index >= 64");
+  if (!sm_count[dev].load()) { int n = 0; B2S_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); sm_count[dev].store(n); }
+  if (!configured[dev].load()) {
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WholeSmem<P>::BYTES));
+    configured[dev].store(true);
+  }
+  const int sms = sm_count[dev].load();
+  const int slots = sms - g_sm_reserve.load() > 0 ? sms - g_sm_reserve.load() : 1;
+  int64_t n_whole = n_images;
+  const int64_t rem = n_images % slots;
+  if (n_images > slots && rem > 0 && 2 * rem <= slots && env_int("B2S_WHOLE_TAIL", 1)) n_whole = n_images - rem;
+  const unsigned grid = (unsigned)(n_whole < slots ? n_whole : slots);
+  kern<<<grid, P::NT, WholeSmem<P>::BYTES, st>>>(pro, epi, scale, (int)n_whole, (int)n_images);
+  int rc = check_launch("fft2_whole_kernel");
+  if (rc || n_whole == n_images) return rc;
+  return launch_fused<P, Pro, Epi, CARRY, REVERSE>(pro, epi, scale, n_images, st, n_whole);
 }
 
 // Paired variant: clusters of two CTAs (one image per cluster at a time), see PhaseA2.
@@ -94,6 +127,9 @@ static int use_pair(int auto_on = 0) {
   return p < 0 ? auto_on : p;
 }
 
+// B2S_DCFIX=0: fused predicated soft-DC epilogue (round 1) instead of the row fix-up (EpiDCFix)
+static int use_dcfix() { return env_int("B2S_DCFIX", 1); }
+
 }  // namespace
 
 // ---- per-plan launch helpers -------------------------------------------------------------------
@@ -105,11 +141,13 @@ int plan_fft2c(const float* in, float* out, int64_t n_images, int inverse, float
   if (inverse) {
     ProPlain<H, W, true> pro{(const cfloat*)in, hw};
     EpiPlain<H, W, true> epi{(cfloat*)out, hw};
+    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) return launch_whole<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, 5, 1, true>(pro, epi, s, n_images, st); }
     if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st); }
     return launch_fused<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st);
   }
   ProPlain<H, W, false> pro{(const cfloat*)in, hw};
   EpiPlain<H, W, false> epi{(cfloat*)out, hw};
+  if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) return launch_whole<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, 5, 1, true>(pro, epi, s, n_images, st); }
   if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st); }
   return launch_fused<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st);
 }
@@ -124,8 +162,15 @@ int plan_expand(const float* image, const float* sens, float* kspace, const floa
 #define B2S_RUN(M)                                                                    \
   {                                                                                   \
     EpiKspace<H, W, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};      \
+    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) return launch_whole<P, ProExpand<H, W>, EpiKspace<H, W, M>, 2, 2>(pro, epi, s, n, st); } \
     if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
     return launch_fused<P>(pro, epi, s, n, st);                                       \
+  }
+  if (mode == 2 && use_dcfix() && (((uintptr_t)kspace | (uintptr_t)ref) & 15) == 0) {
+    // soft DC as a row fix-up behind the plain transform (EpiDCFix); needs 16-byte aligned k-space rows
+    EpiDCFix<H, W> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw, env_int("B2S_DCFIX_PF", 1)};
+    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) return launch_whole<P, ProExpand<H, W>, EpiDCFix<H, W>, 2, 2>(pro, epi, s, n, st); }
+    return launch_fused<P>(pro, epi, s, n, st);
   }
   switch (mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) case 2: B2S_RUN(2) default: B2S_RUN(3) }
 #undef B2S_RUN
@@ -144,6 +189,7 @@ int plan_reduce(const float* kspace, const float* mult, float* out, const uint8_
 #define B2S_RUN(M)                                                      \
   {                                                                     \
     ProKspace<H, W, M> pro{(const cfloat*)kspace, mask, v, c, hw};      \
+    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) return launch_whole<P, ProKspace<H, W, M>, EpiReduce<H, W>, 5, 1, false, true>(pro, epi, s, n, st); } \
     if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
     return launch_fused<P, ProKspace<H, W, M>, EpiReduce<H, W>, false, true>(pro, epi, s, n, st); \
   }
@@ -216,7 +262,8 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
     if (rc || !un) return rc;
   }
   switch (plan_id(h, w)) {
-    case 1: return use_wide(mode != 2) ? plan_expand<P200W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
+    case 1: return (!use_whole() && ((mode == 2 && use_dcfix()) ? env_int("B2S_DCFIX_WIDE", 0) : use_wide(mode != 2)))
+                 ? plan_expand<P200W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
                  : use_quarter() ? plan_expand<P200Q>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
                                  : plan_expand<P200H>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
     case 2: return use_wide(1) ? plan_expand<P256W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)

@@ -102,7 +102,8 @@ template <class P> struct Derived {
   static constexpr int TH_OFF = TW_OFF + P::W;                  // TH[FOLD][G][NKEEP] (every q)
   static constexpr int SMEM_ELEMS = TH_OFF + 8 * P::G;
   static constexpr int MASK_BYTES = (P::H + 15) / 16 * 16;      // this item's mask row (uint8) after the tables
-  static constexpr int SMEM_BYTES = SMEM_ELEMS * 8 + MASK_BYTES;
+  static constexpr int AUX_BYTES = 2 * MASK_BYTES + 16;         // row-fix-up epilogues: mask row + sampled-row list + count,
+  static constexpr int SMEM_BYTES = SMEM_ELEMS * 8 + 2 * AUX_BYTES;   // double-buffered (current and previous work item)
   static constexpr int XP = P::X0 / P::NC;                      // column groups per row group
   static constexpr int TASKS_A = P::G * XP;
   static constexpr int KXP = P::W / P::NCC;

@@ -23,7 +23,7 @@ __device__ unsigned long long g_phase_cycles[8];
 // prefetch use it).
 template <class P, class Pro, class Epi, bool CARRY, bool REVERSE = false>
 __global__ void __launch_bounds__(P::NT, P::CTAS)
-fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_items) {
+fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_items, const int item0) {
   using D = Derived<P>;
   extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
   cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);
@@ -44,22 +44,35 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
   // still cached instead of the part that was evicted first.
   const int n_img = n_items / P::FOLD;
   auto image_of = [&](int item) -> long long { const int n = item / P::FOLD; return REVERSE ? n_img - 1 - n : n; };
-  if (CARRY && (int)blockIdx.x < n_items) PA::prefill(pro, pro.ctx(image_of(blockIdx.x)), tid, queue);
+  if (CARRY && item0 + (int)blockIdx.x < n_items) PA::prefill(pro, pro.ctx(image_of(item0 + blockIdx.x)), tid, queue);
+  static_assert(!Epi::FIXUP || 2 * D::MASK_BYTES + 16 <= D::AUX_BYTES, "aux buffer too small");
+  int cur = 0;                                             // aux buffer of the current item (row fix-up epilogues)
+  long long prev_image = -1;
 
 #pragma unroll 1
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  for (int item = item0 + blockIdx.x; item < n_items; item += gridDim.x) {
     const long long image = image_of(item);
     const int q = item % P::FOLD;
     const int next = item + (int)gridDim.x;
     const bool has_next = next < n_items;
     const long long next_image = has_next ? image_of(next) : image;
     if (!CARRY) PA::prefill(pro, pro.ctx(image), tid, queue);
+    if constexpr (Epi::FIXUP) epi.stage_mask_row(image, mrow + cur * D::AUX_BYTES, tid, P::NT);
     // run<true>: the barrier that protects B (and the mask rows) from the previous item's Phase C sits
     // inside, just before the first write into B, so the first loads of this item are already in flight
     PA::template run<true>(pro, pro.ctx(image), pro.ctx(next_image), CARRY && has_next, smem, q, tid, queue);
     __syncthreads();
-    epi.stage_mask(image, mrow, tid, P::NT);               // visible to Phase C through the barriers below
     B2S_TICK(0);
+    epi.stage_mask(image, mrow, tid, P::NT);               // visible to Phase C through the barriers below
+    if constexpr (Epi::FIXUP) {
+      // every warp has passed the barrier inside Phase A, i.e. has issued all Phase C stores of the previous item:
+      // blend its sampled rows now (its row list sits in the other aux buffer), and list this item's rows
+      epi.template stage_rows<P::FOLD>(q, mrow + cur * D::AUX_BYTES, tid, P::NT - 32);   // last warp: not the one with the ragged Phase C round
+      if (prev_image >= 0) epi.template fixup<P::NT>(prev_image, mrow + (cur ^ 1) * D::AUX_BYTES, tid);
+      prev_image = image;
+      cur ^= 1;
+      B2S_TICK(4);
+    }
     // warm L2 with the rest of the next item while this SM is busy with register codelets (Phases B, C)
     if (has_next && (next % P::FOLD) == 0) pro.l2_prefetch(next_image, tid);
     epi.l2_prefetch(image, q, P::FOLD, tid);                        // what Phase C will read (issued here, not before
@@ -83,6 +96,10 @@ fft2_half_kernel(const Pro pro, const Epi epi, const float scale, const int n_it
       for (int task = tid; task < D::TASKS_C; task += P::NT) phase_c<P>(epi, ectx, smem, q, task, scale);
     }
     B2S_TICK(3);                                           // no barrier here: see run<true>
+  }
+  if constexpr (Epi::FIXUP) {
+    __syncthreads();                                       // last item: its Phase C stores and row list
+    if (prev_image >= 0) epi.template fixup<P::NT>(prev_image, mrow + (cur ^ 1) * D::AUX_BYTES, tid);
   }
 }
 
@@ -148,7 +165,7 @@ void fft2_half_emulate(const Pro& pro, const Epi& epi, float scale, long long n_
   using D = Derived<P>;
   typedef PhaseA<P, Pro> PA;
   cfloat* smem = new cfloat[D::SMEM_ELEMS];
-  uint8_t* mrow = new uint8_t[D::MASK_BYTES];
+  uint8_t* mrow = new uint8_t[2 * D::AUX_BYTES];
   PhaseBRegs<P>* regs = new PhaseBRegs<P>[P::NT];
   typename PA::Queue* queues = new typename PA::Queue[P::NT];
   for (int i = 0; i < D::SMEM_ELEMS; ++i) smem[i] = make_c(0.f, 0.f);
@@ -169,6 +186,11 @@ void fft2_half_emulate(const Pro& pro, const Epi& epi, float scale, long long n_
     }
     for (int tid = 0; tid < P::NT; ++tid)
       for (int task = tid; task < D::TASKS_C; task += P::NT) phase_c<P>(epi, ectx, smem, q, task, scale);
+    if constexpr (Epi::FIXUP) {                                // (the device defers this behind the next item's Phase A)
+      for (int tid = 0; tid < P::NT; ++tid) epi.stage_mask_row(image, mrow, tid, P::NT);
+      for (int tid = 0; tid < P::NT; ++tid) epi.template stage_rows<P::FOLD>(q, mrow, tid, P::NT - 32);
+      for (int tid = 0; tid < P::NT; ++tid) epi.template fixup<P::NT>(image, mrow, tid);
+    }
   }
   delete[] queues;
   delete[] regs;

@@ -189,6 +189,7 @@ template <int H, int W, int WMODE> struct ProKspace {
 
 // ------------------------------ epilogues ---------------------------------- //
 template <int H, int W, bool INV> struct EpiPlain {
+  static constexpr bool FIXUP = false;
   cfloat* out; long long image_stride;
   struct Ctx { cfloat* p; };
   typedef cfloat* Ptr;
@@ -211,6 +212,7 @@ template <int H, int W, bool INV> struct EpiPlain {
 
 // MODE 0: k ; 1: k*m + 0.0 ; 2: (1-m) k + m (k + v ref)/(1+v) ; 3: k*m - ref
 template <int H, int W, int MODE> struct EpiKspace {
+  static constexpr bool FIXUP = false;
   cfloat* out; const cfloat* ref; const uint8_t* mask; const float* vptr; int C; long long hw;
   struct Ctx { cfloat* p; const cfloat* r; const uint8_t* m; float v, inv1v; };
   struct Ptr { cfloat* p; const cfloat* r; const uint8_t* m; float v, inv1v; };
@@ -286,8 +288,116 @@ template <int H, int W, int MODE> struct EpiKspace {
   }
 };
 
+// Soft-DC blend (varnet.py:281-282) as a ROW FIX-UP instead of a predicated epilogue.  Phase C stores the plain
+// transform (no mask look-ups, no predicated reference loads, 50 registers fewer); once every warp of the CTA has
+// left that Phase C (the kernel calls `fixup` behind the next work item's Phase A barrier) the CTA re-reads only the
+// SAMPLED rows of what it just wrote (still in L2) together with the same rows of the reference k-space, blends them
+// and writes them back: 3 x 25 % of the image in fully coalesced 128-bit accesses with ten loads in flight per
+// thread, instead of 25 predicated 64-bit loads per Phase C task that sit in the dependency chain of its stores.
+// `stage_rows` lists, per work item, the sampled rows of its residue class (ky == q mod FOLD).
+template <int H, int W> struct EpiDCFix {
+  static constexpr bool FIXUP = true;
+  static constexpr int V4 = W / 2;                       // 128-bit accesses per row
+  cfloat* out; const cfloat* ref; const uint8_t* mask; const float* vptr; int C; long long hw; int pf;
+  struct Ctx { cfloat* p; };
+  typedef cfloat* Ptr;
+  B2S_HD Ctx ctx(long long image, const uint8_t*) const { Ctx c; c.p = out + image * hw; return c; }
+  // aux layout: [LIST, LIST + H) sampled rows ky == q (mod FOLD) in ascending order, [CNT] their count (int)
+  static constexpr int LIST = (H + 15) / 16 * 16, CNT = 2 * LIST, AUX_BYTES = 2 * LIST + 16;
+  // the item's mask row into aux[0, H): called by every thread BEFORE Phase A (the load latency hides behind it)
+  B2S_HD void stage_mask_row(long long image, uint8_t* aux, int tid, int nt) const {
+    const uint8_t* src = mask + (image / C) * H;
+    for (int y = tid; y < H; y += nt) aux[y] = src[y];
+  }
+  // compaction of the staged row by ONE warp (lanes tid0 .. tid0 + 31) after a barrier
+  template <int FOLD> B2S_HD void stage_rows(int q, uint8_t* aux, int tid, int tid0) const {
+    constexpr int NR = H / FOLD, IT = (NR + 31) / 32;
+#if defined(__CUDA_ARCH__)
+    if (tid >= tid0 && tid < tid0 + 32) {
+      const int lane = tid - tid0;
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < IT; ++i) {
+        const int r = 32 * i + lane;
+        const bool on = (r < NR) && aux[q + FOLD * r];
+        const unsigned bits = __ballot_sync(0xffffffffu, on);
+        if (on) aux[LIST + n + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)(q + FOLD * r);
+        n += __popc(bits);
+      }
+      if (lane == 0) *reinterpret_cast<int*>(aux + CNT) = n;
+    }
+#else
+    if (tid == tid0) {
+      int n = 0;
+      for (int y = q; y < H; y += FOLD) if (aux[y]) aux[LIST + n++] = (uint8_t)y;
+      *reinterpret_cast<int*>(aux + CNT) = n;
+    }
+    (void)IT;
+#endif
+  }
+  B2S_HD void stage_mask(long long, uint8_t*, int, int) const {}
+  B2S_HD Ptr task_ptr(const Ctx& c, int m, int kx) const { return c.p + m * W + kx; }
+  template <int G, int NC> struct Pre {};
+  template <int G, int NC> B2S_HD void prefetch(Ptr, Pre<G, NC>&) const {}
+  template <int G, int NC> B2S_HD void store(Ptr p, int k, const float* re, const float* im, const Pre<G, NC>&) const {
+    cvec<NC> v;
+#pragma unroll
+    for (int n = 0; n < NC; ++n) v.v[n] = make_c(re[n], im[n]);
+    stv<NC>(p + 8 * k * W, v);
+  }
+  // blend the sampled rows listed in aux (written by stage_rows for this image/q)
+  template <int NT> B2S_HD void fixup(long long image, const uint8_t* aux, int tid) const {
+    constexpr int U = 5;
+    if (pf & 16) return;                                  // dev: timing without the fix-up
+    const int total = *reinterpret_cast<const int*>(aux + CNT) * V4;
+    cvec<2>* o = reinterpret_cast<cvec<2>*>(out + image * hw);
+    const cvec<2>* r = reinterpret_cast<const cvec<2>*>(ref + image * hw);
+    const float v = *vptr, inv1v = 1.f / (1.f + v);
+    for (int e0 = tid; e0 < total; e0 += NT * U) {
+      cvec<2> a[U], b[U]; int off[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * NT;
+        off[u] = -1;
+        if (e < total) {
+          const int i = e / V4;
+          off[u] = (int)aux[LIST + i] * V4 + (e - i * V4);
+          a[u] = ldv<2>(reinterpret_cast<const cfloat*>(o + off[u]));
+          b[u] = (pf & 32) ? a[u] : ldv_stream<2>(reinterpret_cast<const cfloat*>(r + off[u]));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (off[u] >= 0) {
+          cvec<2> z;
+#pragma unroll
+          for (int n = 0; n < 2; ++n)
+            z.v[n] = make_c((a[u].v[n].x + v * b[u].v[n].x) * inv1v, (a[u].v[n].y + v * b[u].v[n].y) * inv1v);
+          if (!(pf & 64) || z.v[0].x == 123.456f) stv_stream<2>(reinterpret_cast<cfloat*>(o + off[u]), z);
+        }
+      }
+    }
+  }
+  B2S_HD void l2_prefetch(long long image, int q, int fold, int tid) const {
+    if ((pf & 15) == 1) {
+      const int y = fold * tid + q;
+      if (y < H && mask[(image / C) * H + y]) l2_prefetch_bulk(ref + image * hw + (long long)y * W, W * 8);
+    }
+#if defined(__CUDA_ARCH__)
+    if ((pf & 15) == 2) {                                        // per-thread 128-byte line prefetches: W*8/128 lines per row
+      constexpr int LPR = (W * 8 + 127) / 128;
+      for (int e = tid; e < (H / fold) * LPR; e += 256) {
+        const int r = e / LPR, l = e - r * LPR, y = fold * r + q;
+        if (mask[(image / C) * H + y]) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(ref + image * hw + (long long)y * W) + 128 * l));
+      }
+    }
+#endif
+  }
+};
+
 // out[(b,t,c) . ostride] += conj(mult[(b,t,c) . mstride]) * ifft(k);  zero stride = reduced dim
 template <int H, int W> struct EpiReduce {
+  static constexpr bool FIXUP = false;
   cfloat* out; const cfloat* mult; int T, C;
   long long os_b, os_t, os_c, ms_b, ms_t, ms_c;
   struct Ctx { cfloat* o; const cfloat* m; };

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include "sense_functors.cuh"
 #include "fft2_kernel.cuh"
+#include "fft2_whole.cuh"
 
 using namespace b2s;
 typedef Plan<200, 200, 256, 1, 2> P200;    // half split
@@ -22,8 +23,15 @@ static float norm_scale(int h, int w, int inverse, int norm) {
   return (float)s;
 }
 
-static int g_variant = 0;   // 200x200: 0 half split, 1 half split with 128-bit accesses, 2 quarter split, 3 paired (cluster), 4 wide Phase A
-#define EMULATE(P, pro, epi, scale, n) do { if (g_variant == 3 && P::FOLD == 2 && P::NC == 1) fft2_pair_emulate_if<P>(pro, epi, scale, n); else fft2_half_emulate<P>(pro, epi, scale, n); } while (0)
+static int g_variant = 0;   // 200x200: 0 half split, 1 half split with 128-bit accesses, 2 quarter split, 3 paired (cluster), 4 wide Phase A,
+                            // 5 half split with the soft-DC row fix-up epilogue (EpiDCFix), 6 / 7 whole image (parking lot) with a
+                            // 5- / 2-step load queue (7: soft DC through the row fix-up)
+template <class P, class Pro, class Epi> static void whole_if(const Pro& pro, const Epi& epi, float scale, long long n, int qd) {
+  if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) {
+    if (qd == 5) fft2_whole_emulate<P, Pro, Epi, 5, 1>(pro, epi, scale, n); else fft2_whole_emulate<P, Pro, Epi, 2, 2>(pro, epi, scale, n);
+  } else fft2_half_emulate<P>(pro, epi, scale, n);
+}
+#define EMULATE(P, pro, epi, scale, n) do { if (g_variant == 6 || g_variant == 7) { whole_if<P>(pro, epi, scale, n, g_variant == 6 ? 5 : 2); break; } if (g_variant == 3 && P::FOLD == 2 && P::NC == 1) fft2_pair_emulate_if<P>(pro, epi, scale, n); else fft2_half_emulate<P>(pro, epi, scale, n); } while (0)
 template <class P, class Pro, class Epi> static void fft2_pair_emulate_if(const Pro& pro, const Epi& epi, float scale, long long n) {
   if constexpr (P::FOLD == 2 && P::NC == 1) fft2_pair_emulate<P>(pro, epi, scale, n); else fft2_half_emulate<P>(pro, epi, scale, n);
 }
@@ -51,6 +59,11 @@ template <class P> static int t_expand(const float* img, const float* sens, floa
   const long long hw = (long long)H * W, n = (long long)b * t * c;
   ProExpand<H, W> pro{(const cfloat*)img, (const cfloat*)sens, t, c, hw};
 #define RUN(M) { EpiKspace<H, W, M> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, hw}; EMULATE(P, pro, epi, scale, n); }
+  if (mode == 2 && (g_variant == 5 || g_variant == 7)) {
+    EpiDCFix<H, W> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, hw, 1};
+    if (g_variant == 7) whole_if<P>(pro, epi, scale, n, 2); else fft2_half_emulate<P>(pro, epi, scale, n);
+    return 0;
+  }
   if (mode == 0) RUN(0) else if (mode == 1) RUN(1) else if (mode == 2) RUN(2) else if (mode == 3) RUN(3) else return 1;
 #undef RUN
   return 0;

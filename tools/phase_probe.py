@@ -20,8 +20,8 @@ def probe(name, fn, n=5):
     for _ in range(n): fn()
     lib.b2s_debug_phase_cycles(buf, 1)
     items = n * b * t * c * 2
-    vals = [buf[i] / items for i in range(4)]
-    print(f"{name:16s} cycles/item: A={vals[0]:8.0f} Bread+dft={vals[1]:8.0f} Bwrite={vals[2]:8.0f} C={vals[3]:8.0f} total={sum(vals):8.0f}")
+    vals = [buf[i] / items for i in range(6)]
+    print(f"{name:16s} cycles/item: A={vals[0]:8.0f} Bread+dft={vals[1]:8.0f} Bwrite={vals[2]:8.0f} C={vals[3]:8.0f} fix={vals[4]:8.0f} unpark={vals[5]:8.0f} total={sum(vals):8.0f}")
 probe("fft2c", lambda: ops.raw_fft2c(k, False, 1))
 probe("sens_reduce", lambda: ops.raw_sens_reduce(k, s))
 probe("sens_expand", lambda: ops.raw_sens_expand(x, s))
