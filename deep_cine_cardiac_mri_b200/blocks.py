@@ -314,3 +314,83 @@ def xpd_temporal_ifft(x: torch.Tensor, n_ch: int) -> torch.Tensor:
     z = ops.fft1c(z.contiguous(), "ortho", True)
     z = z.permute(0, 4, 1, 2, 3, 5)
     return torch.cat([z[..., 0], z[..., 1]], dim=-1)
+
+
+# --------------------------------------------------------------------------- #
+# XPDNet cascade bodies (xpdnet.py:295-298, 372-446; recurrent_xpdnet.py:87-150)
+#
+# Buffers are packed [re_0 .. re_{n-1}, im_0 .. im_{n-1}] along the last dim (utils/math.py:97-135).  The reference
+# moves between that packing and torch.complex through real_to_complex_multi_ch / cat / complex_to_real_multi_ch
+# (five to seven copies per block); here every re-packing is ONE gather (`torch.stack` / `torch.cat` of slices) and the
+# operators in between are the fused kernels.
+# --------------------------------------------------------------------------- #
+def _pick(buffer: torch.Tensor, n: int) -> torch.Tensor:
+    """First complex entry of a packed buffer (..., 2n) as a (..., 2) tensor (the operators act on it only:
+    xpdnet.py:127-128, 160-161)."""
+    if buffer.shape[-1] == 2:
+        return buffer
+    return torch.stack([buffer[..., 0], buffer[..., n]], dim=-1)
+
+
+def _append(buffer: torch.Tensor, new: torch.Tensor, n: int) -> torch.Tensor:
+    """Packed buffer (..., 2n) + one complex entry (..., 2) -> packed (..., 2n + 2): what
+    complex_to_real_multi_ch(cat([real_to_complex_multi_ch(buffer, n), real_to_complex_multi_ch(new, 1)])) builds."""
+    return torch.cat([buffer[..., :n], new[..., 0:1], buffer[..., n:], new[..., 1:2]], dim=-1)
+
+
+def _is_measurements_residual(net) -> bool:
+    return getattr(net, "__name__", "") == "measurements_residual"
+
+
+def xpdnet_measurements_residual(self, concat_kspace: torch.Tensor) -> torch.Tensor:
+    """XPDNet.measurements_residual (xpdnet.py:295-298): packed [re_cur, re_ref, im_cur, im_ref] -> cur - ref."""
+    return torch.stack([concat_kspace[..., 0] - concat_kspace[..., 1], concat_kspace[..., 2] - concat_kspace[..., 3]], dim=-1)
+
+
+def _xpd_k_domain(self, index, image_buffer, kspace_buffer, mask, sens_maps, ref_kspace):
+    net = self.kspace_net[index]
+    img = _pick(image_buffer, self.i_buffer_size)
+    if not self.k_buffer_mode and _is_measurements_residual(net):
+        # primal-only: the "k-space net" is the measurement residual, so the whole K block is M A x - y in ONE launch
+        # (forward operator, mask and subtraction fused: B2S_EXPAND_RESIDUAL)
+        return ops.sens_expand(img, sens_maps, ops.EXPAND_RESIDUAL, ref=ref_kspace, mask=mask)
+    fwd = ops.sens_expand(img, sens_maps, ops.EXPAND_MASK, mask=mask) if self.forward_op.masked else ops.sens_expand(img, sens_maps)
+    if self.k_buffer_mode:
+        nd = self.k_buffer_size
+        packed = torch.cat([kspace_buffer[..., :nd], fwd[..., 0:1], ref_kspace[..., 0:1],
+                            kspace_buffer[..., nd:], fwd[..., 1:2], ref_kspace[..., 1:2]], dim=-1)
+    else:
+        packed = torch.cat([fwd[..., 0:1], ref_kspace[..., 0:1], fwd[..., 1:2], ref_kspace[..., 1:2]], dim=-1)
+    return net(packed)
+
+
+def xpdnet_k_domain_correction(self, i_domain, image_buffer, kspace_buffer, mask, sens_maps, ref_kspace):
+    """XPDNetBlock.k_domain_correction (xpdnet.py:372-403)."""
+    return _xpd_k_domain(self, i_domain // 2, image_buffer, kspace_buffer, mask, sens_maps, ref_kspace)
+
+
+def xpdnet_rnn_k_domain_correction(self, i_cascade, image_buffer, kspace_buffer, mask, sens_maps, ref_kspace):
+    """XPDNet_RNN.k_domain_correction (recurrent_xpdnet.py:93-125)."""
+    return _xpd_k_domain(self, i_cascade, image_buffer, kspace_buffer, mask, sens_maps, ref_kspace)
+
+
+def xpdnet_update_image_buffer(self, image_buffer, kspace_buffer, mask, sens_maps):
+    """Head of XPDNetBlock.i_domain_correction (xpdnet.py:419-429) == XPDNet_RNN.update_image_buffer
+    (recurrent_xpdnet.py:128-150): A^H (M r) appended to the packed image buffer."""
+    new = self.backward_op(kspace_buffer, mask, sens_maps, self.k_buffer_size)          # (b,t,1,h,w,2), fused kernel
+    if not self.i_buffer_mode:
+        return new
+    return _append(image_buffer, new, self.i_buffer_size)
+
+
+def xpdnet_i_domain_correction(self, i_domain, image_buffer, kspace_buffer, mask, sens_maps):
+    """XPDNetBlock.i_domain_correction (xpdnet.py:406-446); the image nets are called exactly as the reference does."""
+    image_buffer = xpdnet_update_image_buffer(self, image_buffer, kspace_buffer, mask, sens_maps)
+    b, t, c, h, w, ch = image_buffer.shape
+    ch_out = 2 * self.i_buffer_size
+    if self.dynamic_type in ['XF', 'XT']:
+        return self.xfyf_transform(image_buffer.squeeze(2), i_domain)
+    if self.dynamic_type == '2D':
+        image_in = image_buffer.permute(0, 1, 2, 5, 3, 4).reshape(b * t, c * ch, h, w)
+        return self.image_net[i_domain // 2](image_in).reshape(b, t, c, ch_out, h, w).permute(0, 1, 2, 4, 5, 3)
+    raise ValueError(f"unknown dynamic_type {self.dynamic_type!r}")

@@ -1,10 +1,12 @@
 // Fused single-pass SENSE operators on the plan sizes (200 x 200) and their
 // composition from the generic kernels for every other size.
 #include <stdlib.h>
+#include <type_traits>
 #include "b2s_common.cuh"
 #include "sense_functors.cuh"
 #include "fft2_kernel.cuh"
 #include "fft2_whole.cuh"
+#include "fft2_packed.cuh"
 
 using namespace b2s;
 
@@ -17,7 +19,10 @@ typedef Plan<200, 200, 256, 2, 2, 1> P200W; // half split, 128-bit Phase A loads
 typedef Plan<256, 256, 256, 2, 4, 1> P256W; // quarter split, 128-bit Phase A loads
 constexpr int W256_PLAIN = 0;
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
-static int use_whole() { return env_int("B2S_WHOLE", 1); }   // 200 x 200: whole-image kernel with the TMEM parking lot               // auto choice of P256W for fft2c / sens_reduce (sens_expand: always)
+static int use_whole() { return env_int("B2S_WHOLE", 1); }   // 200 x 200: whole-image kernel with the TMEM parking lot
+static int use_packed() { return env_int("B2S_PACKED", 1); } // ... with packed two-transform arithmetic (fft2_packed.cuh)
+#define B2S_WHOLE(PRO, EPI, QD, TT, CARRY, REV, pro, epi, s, n, st) \
+  (use_packed() ? launch_whole<P, PRO, EPI, QD, TT, CARRY, REV, true>(pro, epi, s, n, st) : launch_whole<P, PRO, EPI, QD, TT, CARRY, REV, false>(pro, epi, s, n, st))               // auto choice of P256W for fft2c / sens_reduce (sens_expand: always)
 
 // B2S_WIDE: unset/-1 = auto (128-bit Phase A only where it measured faster: the two-stream sens_expand
 // without the DC epilogue, 148 vs 162 us), 0 = never, 1 = always.
@@ -62,11 +67,16 @@ int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, 
 // Whole-image kernel (fft2_whole.cuh, TMEM parking lot) on as many images as fill whole rounds of the persistent
 // grid; a remainder that fits one round of half items (2 * rem <= CTAs) goes through the half-split kernel behind it
 // (a ragged last round of whole images would idle most SMs for a full image time).
-template <class P, class Pro, class Epi, int QD, int TT, bool CARRY = false, bool REVERSE = false>
-int launch_whole(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st) {
+template <class P, class Pro, class Epi, int QD, int TT, bool CARRY = false, bool REVERSE = false, bool PACKED = false, class TailEpi = Epi>
+int launch_whole(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st, const TailEpi* tail_epi = nullptr) {
   if (n_images <= 0) return B2S_OK;
   if (2 * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
-  auto kern = fft2_whole_kernel<P, Pro, Epi, QD, TT, CARRY, REVERSE>;
+  typedef PackPlan200<256> PP;
+  static_assert(!PACKED || (P::H == 200 && P::W == 200), "packed kernel: 200 x 200 only");
+  constexpr int SMEM = PACKED ? PkSmem<PP, Epi>::BYTES : WholeSmem<P>::BYTES;
+  void (*kern)(const Pro, const Epi, const float, const int, const int, const int, const int);
+  if constexpr (PACKED) kern = fft2_packed_kernel<PP, Pro, Epi, QD, TT, CARRY, REVERSE>;
+  else kern = fft2_whole_kernel<P, Pro, Epi, QD, TT, CARRY, REVERSE>;
   int dev = 0;
   B2S_CUDA(cudaGetDevice(&dev));
   static std::atomic<int> sm_count[64];
@@ -74,7 +84,7 @@ int launch_whole(const Pro& pro, const Epi& epi, float scale, int64_t n_images, 
   if (dev < 0 || dev >= 64) return fail(B2S_EUNSUPPORTED, "device index >= 64");
   if (!sm_count[dev].load()) { int n = 0; B2S_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); sm_count[dev].store(n); }
   if (!configured[dev].load()) {
-    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WholeSmem<P>::BYTES));
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured[dev].store(true);
   }
   const int sms = sm_count[dev].load();
@@ -83,10 +93,11 @@ int launch_whole(const Pro& pro, const Epi& epi, float scale, int64_t n_images, 
   const int64_t rem = n_images % slots;
   if (n_images > slots && rem > 0 && 2 * rem <= slots && env_int("B2S_WHOLE_TAIL", 1)) n_whole = n_images - rem;
   const unsigned grid = (unsigned)(n_whole < slots ? n_whole : slots);
-  kern<<<grid, P::NT, WholeSmem<P>::BYTES, st>>>(pro, epi, scale, (int)n_whole, (int)n_images);
+  kern<<<grid, P::NT, SMEM, st>>>(pro, epi, scale, (int)n_whole, (int)n_images, env_int("B2S_AHEAD", 1), env_int("B2S_CDUAL", 0));
   int rc = check_launch("fft2_whole_kernel");
   if (rc || n_whole == n_images) return rc;
-  return launch_fused<P, Pro, Epi, CARRY, REVERSE>(pro, epi, scale, n_images, st, n_whole);
+  if constexpr (std::is_same<TailEpi, Epi>::value) return launch_fused<P, Pro, Epi, CARRY, REVERSE>(pro, epi, scale, n_images, st, n_whole);
+  else return launch_fused<P, Pro, TailEpi, CARRY, REVERSE>(pro, *tail_epi, scale, n_images, st, n_whole);
 }
 
 // Paired variant: clusters of two CTAs (one image per cluster at a time), see PhaseA2.
@@ -128,7 +139,7 @@ static int use_pair(int auto_on = 0) {
 }
 
 // B2S_DCFIX=0: fused predicated soft-DC epilogue (round 1) instead of the row fix-up (EpiDCFix)
-static int use_dcfix() { return env_int("B2S_DCFIX", 1); }
+static int use_dcfix() { return env_int("B2S_DCFIX", 0); }
 
 }  // namespace
 
@@ -141,13 +152,13 @@ int plan_fft2c(const float* in, float* out, int64_t n_images, int inverse, float
   if (inverse) {
     ProPlain<H, W, true> pro{(const cfloat*)in, hw};
     EpiPlain<H, W, true> epi{(cfloat*)out, hw};
-    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) return launch_whole<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, 5, 1, true>(pro, epi, s, n_images, st); }
+    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) { typedef ProPlain<H, W, true> PR; typedef EpiPlain<H, W, true> EP; return B2S_WHOLE(PR, EP, 5, 1, true, false, pro, epi, s, n_images, st); } }
     if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st); }
     return launch_fused<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st);
   }
   ProPlain<H, W, false> pro{(const cfloat*)in, hw};
   EpiPlain<H, W, false> epi{(cfloat*)out, hw};
-  if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) return launch_whole<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, 5, 1, true>(pro, epi, s, n_images, st); }
+  if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) { typedef ProPlain<H, W, false> PR; typedef EpiPlain<H, W, false> EP; return B2S_WHOLE(PR, EP, 5, 1, true, false, pro, epi, s, n_images, st); } }
   if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st); }
   return launch_fused<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st);
 }
@@ -162,14 +173,22 @@ int plan_expand(const float* image, const float* sens, float* kspace, const floa
 #define B2S_RUN(M)                                                                    \
   {                                                                                   \
     EpiKspace<H, W, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};      \
-    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) return launch_whole<P, ProExpand<H, W>, EpiKspace<H, W, M>, 2, 2>(pro, epi, s, n, st); } \
+    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) { typedef ProExpand<H, W> PR; typedef EpiKspace<H, W, M> EP; return B2S_WHOLE(PR, EP, 2, 2, false, false, pro, epi, s, n, st); } } \
     if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
     return launch_fused<P>(pro, epi, s, n, st);                                       \
   }
+  if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) {
+    // soft DC on the packed whole-image kernel with the reference rows staged in shared memory by the bulk-copy engine
+    if (mode == 2 && use_whole() && use_packed() && env_int("B2S_DCSTAGE", 1) && ((uintptr_t)ref & 15) == 0) {
+      EpiDCStage<H, W> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};
+      EpiKspace<H, W, 2> tail{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};
+      return launch_whole<P, ProExpand<H, W>, EpiDCStage<H, W>, 2, 2, false, false, true, EpiKspace<H, W, 2>>(pro, epi, s, n, st, &tail);
+    }
+  }
   if (mode == 2 && use_dcfix() && (((uintptr_t)kspace | (uintptr_t)ref) & 15) == 0) {
     // soft DC as a row fix-up behind the plain transform (EpiDCFix); needs 16-byte aligned k-space rows
-    EpiDCFix<H, W> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw, env_int("B2S_DCFIX_PF", 1)};
-    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) return launch_whole<P, ProExpand<H, W>, EpiDCFix<H, W>, 2, 2>(pro, epi, s, n, st); }
+    EpiDCFix<H, W> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw, env_int("B2S_DCFIX_PF", 3)};
+    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) { typedef ProExpand<H, W> PR; typedef EpiDCFix<H, W> EP; return B2S_WHOLE(PR, EP, 2, 2, false, false, pro, epi, s, n, st); } }
     return launch_fused<P>(pro, epi, s, n, st);
   }
   switch (mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) case 2: B2S_RUN(2) default: B2S_RUN(3) }
@@ -189,7 +208,7 @@ int plan_reduce(const float* kspace, const float* mult, float* out, const uint8_
 #define B2S_RUN(M)                                                      \
   {                                                                     \
     ProKspace<H, W, M> pro{(const cfloat*)kspace, mask, v, c, hw};      \
-    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) return launch_whole<P, ProKspace<H, W, M>, EpiReduce<H, W>, 5, 1, false, true>(pro, epi, s, n, st); } \
+    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) { typedef ProKspace<H, W, M> PR; typedef EpiReduce<H, W> EP; return B2S_WHOLE(PR, EP, 5, 1, false, true, pro, epi, s, n, st); } } \
     if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
     return launch_fused<P, ProKspace<H, W, M>, EpiReduce<H, W>, false, true>(pro, epi, s, n, st); \
   }

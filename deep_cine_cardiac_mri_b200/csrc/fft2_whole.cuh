@@ -214,7 +214,7 @@ template <class P> struct WholeSmem { static constexpr int BYTES = Derived<P>::S
 
 template <class P, class Pro, class Epi, int QD, int TT, bool CARRY, bool REVERSE = false>
 __global__ void __launch_bounds__(P::NT, 1)
-fft2_whole_kernel(const Pro pro, const Epi epi, const float scale, const int n_images, const int n_total) {
+fft2_whole_kernel(const Pro pro, const Epi epi, const float scale, const int n_images, const int n_total, const int, const int) {
   using D = Derived<P>;
   extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
   cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);

@@ -95,6 +95,23 @@ B2S_HD void prefetch_span(const void* base, long long bytes, int tid) {
   if (off < bytes) l2_prefetch_bulk((const char*)base + off, (unsigned)((bytes - off) < chunk ? (bytes - off) : chunk));
 }
 
+// Sampled rows of the reference k-space of `image` into L2, one 128-byte line per instruction through the ordinary
+// load/store path (the per-SM bulk-copy unit needs ~600 cycles per 1600-byte row whatever its size: 50 rows per image
+// would outlast the image).  Called one image AHEAD of their use, with evict_last so that the streamed output does
+// not push them out again.
+template <int H, int W>
+B2S_HD void prefetch_sampled_rows(const cfloat* ref_image, const uint8_t* mask_row, int tid, int nt) {
+#if defined(__CUDA_ARCH__)
+  constexpr int LPR = (W * 8 + 127) / 128;
+  for (int e = tid; e < H * LPR; e += nt) {
+    const int y = e / LPR, l = e - y * LPR;
+    if (mask_row[y]) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"((const char*)(ref_image + (long long)y * W) + 128 * l));
+  }
+#else
+  (void)ref_image; (void)mask_row; (void)tid; (void)nt;
+#endif
+}
+
 // ------------------------------ prologues ---------------------------------- //
 template <int H, int W, bool INV> struct ProPlain {
   const cfloat* in; long long image_stride;
@@ -208,6 +225,7 @@ template <int H, int W, bool INV> struct EpiPlain {
     stv<NC>(p + 8 * k * W, v);
   }
   B2S_HD void l2_prefetch(long long, int, int, int) const {}
+  B2S_HD void l2_prefetch_ahead(long long, int, int) const {}
 };
 
 // MODE 0: k ; 1: k*m + 0.0 ; 2: (1-m) k + m (k + v ref)/(1+v) ; 3: k*m - ref
@@ -279,6 +297,11 @@ template <int H, int W, int MODE> struct EpiKspace {
   // the reference k-space this item will blend with (whole image: the sibling half needs the rest)
   // DC (MODE 2) blends on sampled rows only: warm L2 with just those rows of this work item (ky = q mod
   // fold), W*8 bytes each; MODE 3 reads every row.
+  // whole-image kernels: the NEXT image's sampled reference rows (MODE 2), see prefetch_sampled_rows
+  B2S_HD void l2_prefetch_ahead(long long image, int tid, int nt) const {
+    if (MODE == 2) prefetch_sampled_rows<H, W>(ref + image * hw, mask + (image / C) * H, tid, nt);
+    if (MODE == 3) prefetch_span(ref + image * hw, (long long)H * W * 8, tid);
+  }
   B2S_HD void l2_prefetch(long long image, int q, int fold, int tid) const {
     if (MODE == 3) { if (q == 0) prefetch_span(ref + image * hw, (long long)H * W * 8, tid); }
     if (MODE == 2) {
@@ -288,6 +311,9 @@ template <int H, int W, int MODE> struct EpiKspace {
   }
 };
 
+#ifndef B2S_FIX_U
+#define B2S_FIX_U 10
+#endif
 // Soft-DC blend (varnet.py:281-282) as a ROW FIX-UP instead of a predicated epilogue.  Phase C stores the plain
 // transform (no mask look-ups, no predicated reference loads, 50 registers fewer); once every warp of the CTA has
 // left that Phase C (the kernel calls `fixup` behind the next work item's Phase A barrier) the CTA re-reads only the
@@ -302,16 +328,18 @@ template <int H, int W> struct EpiDCFix {
   struct Ctx { cfloat* p; };
   typedef cfloat* Ptr;
   B2S_HD Ctx ctx(long long image, const uint8_t*) const { Ctx c; c.p = out + image * hw; return c; }
-  // aux layout: [LIST, LIST + H) sampled rows ky == q (mod FOLD) in ascending order, [CNT] their count (int)
-  static constexpr int LIST = (H + 15) / 16 * 16, CNT = 2 * LIST, AUX_BYTES = 2 * LIST + 16;
+  // aux layout: [0, H) the image's mask row; two row lists (slots) of up to H/2 sampled rows each (or ONE list of up to
+  // H rows in slot 0); [CNT + 4*slot] their counts
+  static constexpr int LIST = (H + 15) / 16 * 16, HALF = LIST / 2, CNT = 2 * LIST, AUX_BYTES = 2 * LIST + 16;
   // the item's mask row into aux[0, H): called by every thread BEFORE Phase A (the load latency hides behind it)
   B2S_HD void stage_mask_row(long long image, uint8_t* aux, int tid, int nt) const {
     const uint8_t* src = mask + (image / C) * H;
     for (int y = tid; y < H; y += nt) aux[y] = src[y];
   }
-  // compaction of the staged row by ONE warp (lanes tid0 .. tid0 + 31) after a barrier
-  template <int FOLD> B2S_HD void stage_rows(int q, uint8_t* aux, int tid, int tid0) const {
+  // compaction of the staged row by ONE warp (lanes tid0 .. tid0 + 31) after a barrier: rows q, q + FOLD, ... -> list `slot`
+  template <int FOLD> B2S_HD void stage_rows(int q, uint8_t* aux, int tid, int tid0, int slot = 0) const {
     constexpr int NR = H / FOLD, IT = (NR + 31) / 32;
+    uint8_t* list = aux + LIST + slot * HALF;
 #if defined(__CUDA_ARCH__)
     if (tid >= tid0 && tid < tid0 + 32) {
       const int lane = tid - tid0;
@@ -321,16 +349,16 @@ template <int H, int W> struct EpiDCFix {
         const int r = 32 * i + lane;
         const bool on = (r < NR) && aux[q + FOLD * r];
         const unsigned bits = __ballot_sync(0xffffffffu, on);
-        if (on) aux[LIST + n + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)(q + FOLD * r);
+        if (on) list[n + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)(q + FOLD * r);
         n += __popc(bits);
       }
-      if (lane == 0) *reinterpret_cast<int*>(aux + CNT) = n;
+      if (lane == 0) reinterpret_cast<int*>(aux + CNT)[slot] = n;
     }
 #else
     if (tid == tid0) {
       int n = 0;
-      for (int y = q; y < H; y += FOLD) if (aux[y]) aux[LIST + n++] = (uint8_t)y;
-      *reinterpret_cast<int*>(aux + CNT) = n;
+      for (int y = q; y < H; y += FOLD) if (aux[y]) list[n++] = (uint8_t)y;
+      reinterpret_cast<int*>(aux + CNT)[slot] = n;
     }
     (void)IT;
 #endif
@@ -346,10 +374,18 @@ template <int H, int W> struct EpiDCFix {
     stv<NC>(p + 8 * k * W, v);
   }
   // blend the sampled rows listed in aux (written by stage_rows for this image/q)
-  template <int NT> B2S_HD void fixup(long long image, const uint8_t* aux, int tid) const {
-    constexpr int U = 5;
+  // (not inlined on the device: its 80-100 registers of loads in flight then do not weigh on the allocation of the
+  // persistent loop it is called from)
+#if defined(__CUDACC__)
+  template <int NT> __host__ __device__ __noinline__ void fixup(long long image, const uint8_t* aux, int tid, int slot = 0) const {
+#else
+  template <int NT> void fixup(long long image, const uint8_t* aux, int tid, int slot = 0) const {
+#endif
+    constexpr int U = B2S_FIX_U;                          // 128-bit load PAIRS in flight per thread (the phase owns the whole
+                                                          // register file: nothing else is live between Phases A and B)
     if (pf & 16) return;                                  // dev: timing without the fix-up
-    const int total = *reinterpret_cast<const int*>(aux + CNT) * V4;
+    const int total = reinterpret_cast<const int*>(aux + CNT)[slot] * V4;
+    const uint8_t* list = aux + LIST + slot * HALF;
     cvec<2>* o = reinterpret_cast<cvec<2>*>(out + image * hw);
     const cvec<2>* r = reinterpret_cast<const cvec<2>*>(ref + image * hw);
     const float v = *vptr, inv1v = 1.f / (1.f + v);
@@ -361,7 +397,7 @@ template <int H, int W> struct EpiDCFix {
         off[u] = -1;
         if (e < total) {
           const int i = e / V4;
-          off[u] = (int)aux[LIST + i] * V4 + (e - i * V4);
+          off[u] = (int)list[i] * V4 + (e - i * V4);
           a[u] = ldv<2>(reinterpret_cast<const cfloat*>(o + off[u]));
           b[u] = (pf & 32) ? a[u] : ldv_stream<2>(reinterpret_cast<const cfloat*>(r + off[u]));
         }
@@ -377,6 +413,9 @@ template <int H, int W> struct EpiDCFix {
         }
       }
     }
+  }
+  B2S_HD void l2_prefetch_ahead(long long image, int tid, int nt) const {
+    if ((pf & 15) == 3) prefetch_sampled_rows<H, W>(ref + image * hw, mask + (image / C) * H, tid, nt);
   }
   B2S_HD void l2_prefetch(long long image, int q, int fold, int tid) const {
     if ((pf & 15) == 1) {
@@ -426,6 +465,7 @@ template <int H, int W> struct EpiReduce {
     red_add<NC>(t.o + 8 * k * W, ar, ai);
   }
   B2S_HD void l2_prefetch(long long, int, int, int) const {}
+  B2S_HD void l2_prefetch_ahead(long long, int, int) const {}
 };
 
 }  // namespace b2s

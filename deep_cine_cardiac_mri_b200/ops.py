@@ -75,9 +75,6 @@ def _vdev(v, device) -> torch.Tensor:
     return torch.full((1,), float(v), dtype=torch.float32, device=device)
 
 
-_scratch = {}
-
-
 _force_deterministic = False
 
 
@@ -130,15 +127,13 @@ def upload_masked_kspace(kspace_host: torch.Tensor, mask_dev: torch.Tensor, out:
 
 
 def _scratch_for(b, t, c, h, w, device, full=False):
+    """Scratch for one call (deterministic coil sum, shapes without a fused plan).  Allocated per call on the current
+    stream: torch's caching allocator then owns the stream / CUDA-graph-pool bookkeeping, so concurrent streams
+    (pipeline.varnet_hot_path_streams) and captured graphs never share or outlive a buffer (a per-device cache did)."""
     n = b * t * c * h * w * 8 if full else _lib.lib().b2s_scratch_bytes(b, t, c, h, w)
     if n == 0:
         return None, 0
-    key = (device.index, "s")
-    buf = _scratch.get(key)
-    if buf is None or buf.numel() < n:
-        buf = torch.empty(n, dtype=torch.uint8, device=device)
-        _scratch[key] = buf
-    return buf, n
+    return torch.empty(n, dtype=torch.uint8, device=device), n
 
 
 # --------------------------------------------------------------------------- #
@@ -417,6 +412,9 @@ class NormalOpFn(torch.autograd.Function):
         x, sens, mask_u8, v = ctx.saved_tensors
         g = _f32c(g)
         need = ctx.needs_input_grad
+        if need[1]:
+            raise RuntimeError("NormalOpFn: no gradient w.r.t. the sensitivity maps here; ops.normal_op composes "
+                               "sens_expand / sens_reduce when sens requires grad")
         gx = NormalOpFn.apply(g, sens, mask_u8, v) if need[0] else None
         gv = raw_dot(g, x) if need[3] else None
         return gx, None, None, gv

@@ -116,6 +116,13 @@ def patch_reference(functional: bool = True, block_methods: bool = True):
     _set(xpdnet.SensitivityModel, "forward", blocks.xpdnet_sens_model_forward)
     _set(xpdnet.SensitivityModel, "divide_root_sum_of_squares", blocks.divide_root_sum_of_squares)
     _set(xpdnet.XPDNetBlock, "xfyf_transform", _xpdnet_xfyf_factory(rec))
+    _set(xpdnet.XPDNetBlock, "k_domain_correction", blocks.xpdnet_k_domain_correction)
+    _set(xpdnet.XPDNetBlock, "i_domain_correction", blocks.xpdnet_i_domain_correction)
+    _set(xpdnet.XPDNet, "measurements_residual", blocks.xpdnet_measurements_residual)
+    rxpd = importlib.import_module("reconstruction.models.recurrent_xpdnet")
+    _set(rxpd.XPDNet_RNN, "k_domain_correction", blocks.xpdnet_rnn_k_domain_correction)
+    _set(rxpd.XPDNet_RNN, "update_image_buffer", blocks.xpdnet_update_image_buffer)
+    _set(rxpd.XPDNet_RNN, "measurements_residual", blocks.xpdnet_measurements_residual)
 
     _set(rvar.VarNet_RNN, "sens_expand", blocks.varnet_rnn_sens_expand)
     _set(rvar.VarNet_RNN, "sens_reduce", blocks.varnet_rnn_sens_reduce)

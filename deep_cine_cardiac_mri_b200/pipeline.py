@@ -103,7 +103,9 @@ def varnet_hot_path_image_domain(masked_kspace: torch.Tensor, mask: torch.Tensor
     vs = [x.detach().reshape(1) if isinstance(x, torch.Tensor) else ops._vdev(x, masked_kspace.device) for x in vs]
     ssq = F.complex_abs_sq(s5).sum(dim=1).contiguous()                     # (b,h,w)  sum_c |S_c|^2
     bref = ops.raw_sens_reduce(ops._f32c(masked_kspace), s5, ops.REDUCE_MASK, False, m8, None, 1)   # A^H M ref
-    img = bref                                                             # cascade 0 starts from k = ref
+    # cascade 0 starts from k = ref, i.e. from A^H k with NO mask (varnet.py:253), exactly like varnet_hot_path and the
+    # reference; equal to bref only when the unsampled rows of the input really are zero
+    img = ops.raw_sens_reduce(ops._f32c(masked_kspace), s5, ops.REDUCE_PLAIN, False, None, None, 1)
     for i in range(n_cascades):
         x, mean = ops.raw_temporal_pre(img, xf)
         if regulariser is not None:

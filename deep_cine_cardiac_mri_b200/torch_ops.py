@@ -137,6 +137,9 @@ def _normal_setup(ctx, inputs, output):
 def _normal_bwd(ctx, g):
     x, sens, mask, v = ctx.saved_tensors
     need = ctx.needs_input_grad
+    if need[1]:
+        raise RuntimeError("b200sense.normal_op: gradient w.r.t. the sensitivity maps is not provided by the on-chip normal "
+                           "operator; use ops.normal_op (it composes sens_expand / sens_reduce when sens requires grad)")
     gx = torch.ops.b200sense.normal_op(g.contiguous(), sens, mask, v) if need[0] else None     # H is self-adjoint
     gv = ops.raw_dot(g.contiguous(), x.contiguous()) if need[3] else None
     return gx, None, None, gv

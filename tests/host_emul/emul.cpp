@@ -5,6 +5,7 @@
 #include "sense_functors.cuh"
 #include "fft2_kernel.cuh"
 #include "fft2_whole.cuh"
+#include "fft2_packed.cuh"
 
 using namespace b2s;
 typedef Plan<200, 200, 256, 1, 2> P200;    // half split
@@ -25,13 +26,19 @@ static float norm_scale(int h, int w, int inverse, int norm) {
 
 static int g_variant = 0;   // 200x200: 0 half split, 1 half split with 128-bit accesses, 2 quarter split, 3 paired (cluster), 4 wide Phase A,
                             // 5 half split with the soft-DC row fix-up epilogue (EpiDCFix), 6 / 7 whole image (parking lot) with a
-                            // 5- / 2-step load queue (7: soft DC through the row fix-up)
+                            // 5- / 2-step load queue (7: soft DC through the row fix-up), 8 / 9 the same with packed two-transform arithmetic
 template <class P, class Pro, class Epi> static void whole_if(const Pro& pro, const Epi& epi, float scale, long long n, int qd) {
   if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) {
     if (qd == 5) fft2_whole_emulate<P, Pro, Epi, 5, 1>(pro, epi, scale, n); else fft2_whole_emulate<P, Pro, Epi, 2, 2>(pro, epi, scale, n);
   } else fft2_half_emulate<P>(pro, epi, scale, n);
 }
-#define EMULATE(P, pro, epi, scale, n) do { if (g_variant == 6 || g_variant == 7) { whole_if<P>(pro, epi, scale, n, g_variant == 6 ? 5 : 2); break; } if (g_variant == 3 && P::FOLD == 2 && P::NC == 1) fft2_pair_emulate_if<P>(pro, epi, scale, n); else fft2_half_emulate<P>(pro, epi, scale, n); } while (0)
+template <class P, class Pro, class Epi> static void packed_if(const Pro& pro, const Epi& epi, float scale, long long n, int qd) {
+  if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) {
+    typedef PackPlan200<256> PP;
+    if (qd == 5) fft2_packed_emulate<PP, Pro, Epi, 5, 1>(pro, epi, scale, n); else fft2_packed_emulate<PP, Pro, Epi, 2, 2>(pro, epi, scale, n);
+  } else fft2_half_emulate<P>(pro, epi, scale, n);
+}
+#define EMULATE(P, pro, epi, scale, n) do { if (g_variant >= 8 && g_variant <= 12) { packed_if<P>(pro, epi, scale, n, g_variant == 8 ? 5 : 2); break; } if (g_variant == 6 || g_variant == 7) { whole_if<P>(pro, epi, scale, n, g_variant == 6 ? 5 : 2); break; } if (g_variant == 3 && P::FOLD == 2 && P::NC == 1) fft2_pair_emulate_if<P>(pro, epi, scale, n); else fft2_half_emulate<P>(pro, epi, scale, n); } while (0)
 template <class P, class Pro, class Epi> static void fft2_pair_emulate_if(const Pro& pro, const Epi& epi, float scale, long long n) {
   if constexpr (P::FOLD == 2 && P::NC == 1) fft2_pair_emulate<P>(pro, epi, scale, n); else fft2_half_emulate<P>(pro, epi, scale, n);
 }
@@ -59,9 +66,16 @@ template <class P> static int t_expand(const float* img, const float* sens, floa
   const long long hw = (long long)H * W, n = (long long)b * t * c;
   ProExpand<H, W> pro{(const cfloat*)img, (const cfloat*)sens, t, c, hw};
 #define RUN(M) { EpiKspace<H, W, M> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, hw}; EMULATE(P, pro, epi, scale, n); }
-  if (mode == 2 && (g_variant == 5 || g_variant == 7)) {
+  if (mode == 2 && (g_variant >= 10 && g_variant <= 12)) {   // packed whole-image kernel, staged soft DC (11: capacity 3 + 3 rows -> general path, 12: 14 + 12 rows -> rows in the holes of B)
+    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) {
+      EpiDCStage<H, W> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, hw};
+      fft2_packed_emulate<PackPlan200<256>, ProExpand<H, W>, EpiDCStage<H, W>, 2, 2>(pro, epi, scale, n, g_variant == 11 ? 3 : g_variant == 12 ? 14 : 0);
+      return 0;
+    }
+  }
+  if (mode == 2 && (g_variant == 5 || g_variant == 7 || g_variant == 9)) {
     EpiDCFix<H, W> epi{(cfloat*)kout, (const cfloat*)ref, mask, v, c, hw, 1};
-    if (g_variant == 7) whole_if<P>(pro, epi, scale, n, 2); else fft2_half_emulate<P>(pro, epi, scale, n);
+    if (g_variant == 9) packed_if<P>(pro, epi, scale, n, 2); else if (g_variant == 7) whole_if<P>(pro, epi, scale, n, 2); else fft2_half_emulate<P>(pro, epi, scale, n);
     return 0;
   }
   if (mode == 0) RUN(0) else if (mode == 1) RUN(1) else if (mode == 2) RUN(2) else if (mode == 3) RUN(3) else return 1;

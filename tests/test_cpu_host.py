@@ -120,7 +120,7 @@ def test_generated_codelets(emu):
     assert emu.emu_codelet_worst_error() <= 2e-7          # dft2 ... dft40 vs a direct double DFT
 
 
-@pytest.mark.parametrize("variant,hw", [(0, 200), (1, 200), (2, 200), (3, 200), (4, 200), (6, 200), (7, 200), (0, 256), (4, 256)])
+@pytest.mark.parametrize("variant,hw", [(0, 200), (1, 200), (2, 200), (3, 200), (4, 200), (6, 200), (7, 200), (8, 200), (9, 200), (0, 256), (4, 256)])
 def test_emulated_fft2c(emu, variant, hw):
     emu.emu_set_variant(variant)
     x = G.rng_normal(1, (2, hw, hw, 2))
@@ -132,7 +132,7 @@ def test_emulated_fft2c(emu, variant, hw):
     assert emu.emu_fft2c(P(x), P(x), ctypes.c_longlong(1), 128, 128, 0, 1) == 2     # no plan -> EUNSUPPORTED
 
 
-@pytest.mark.parametrize("variant,hw", [(0, 200), (1, 200), (2, 200), (3, 200), (4, 200), (5, 200), (6, 200), (7, 200), (0, 256), (4, 256), (5, 256)])
+@pytest.mark.parametrize("variant,hw", [(0, 200), (1, 200), (2, 200), (3, 200), (4, 200), (5, 200), (6, 200), (7, 200), (8, 200), (9, 200), (10, 200), (11, 200), (12, 200), (0, 256), (4, 256), (5, 256)])
 def test_emulated_sense_operators(emu, variant, hw):
     emu.emu_set_variant(variant)
     b, t, c, h, w = 2, 2, 3, hw, hw

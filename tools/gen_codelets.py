@@ -216,8 +216,10 @@ def fl(c):
 
 
 def emit(n, d, outs, live, cost, factors):
+    """One codelet, generic over the value type V: float (one transform) or f2 (two independent transforms in the
+    two halves of a 64-bit register pair -> packed FADD2 / FMUL2 / FFMA2 on sm_100a, see packed.cuh)."""
     L = [f"// dft{n}: factors {factors}, {cost} fp32 ops ({cost / n:.1f}/point)",
-         f"B2S_HD void dft{n}(float (&re)[{n}], float (&im)[{n}]) {{"]
+         f"template <class V> B2S_HD void dft{n}(V (&re)[{n}], V (&im)[{n}]) {{"]
     name = {}
     for i, node in enumerate(d.nodes):
         if i not in live:
@@ -228,17 +230,17 @@ def emit(n, d, outs, live, cost, factors):
             continue
         name[i] = f"t{i}"
         if op == "add":
-            e = f"{name[node[1]]} + {name[node[2]]}"
+            e = f"vadd({name[node[1]]}, {name[node[2]]})"
         elif op == "sub":
-            e = f"{name[node[1]]} - {name[node[2]]}"
+            e = f"vsub({name[node[1]]}, {name[node[2]]})"
         elif op == "mul":
-            e = f"{fl(node[1])} * {name[node[2]]}"
+            e = f"vmul({fl(node[1])}, {name[node[2]]})"
         else:
-            e = f"fmaf({fl(node[1])}, {name[node[2]]}, {name[node[3]]})"
-        L.append(f"  const float t{i} = {e};")
+            e = f"vfma({fl(node[1])}, {name[node[2]]}, {name[node[3]]})"
+        L.append(f"  const V t{i} = {e};")
     for k, ((sr, nr), (si, ni)) in enumerate(outs):
-        L.append(f"  const float o{k}r = {'-' if sr < 0 else ''}{name[nr]};"
-                 f" const float o{k}i = {'-' if si < 0 else ''}{name[ni]};")
+        L.append(f"  const V o{k}r = {'vneg(' + name[nr] + ')' if sr < 0 else name[nr]};"
+                 f" const V o{k}i = {'vneg(' + name[ni] + ')' if si < 0 else name[ni]};")
     for k in range(n):
         L.append(f"  re[{k}] = o{k}r; im[{k}] = o{k}i;")
     L.append("}")
@@ -257,6 +259,7 @@ def main():
              "#endif",
              "#endif",
              "#include <math.h>",
+             '#include "packed.cuh"',
              "namespace b2s {", ""]
     summary = []
     for n in SIZES:
@@ -272,8 +275,8 @@ def main():
         summary.append((n, perm, cost))
     parts.append("template <int N> struct Dft;")
     for n in SIZES:
-        parts.append(f"template <> struct Dft<{n}> {{ static B2S_HD void run(float (&re)[{n}], float (&im)[{n}]) {{ dft{n}(re, im); }} }};")
-    parts.append("template <> struct Dft<1> { static B2S_HD void run(float (&)[1], float (&)[1]) {} };")
+        parts.append(f"template <> struct Dft<{n}> {{ template <class V> static B2S_HD void run(V (&re)[{n}], V (&im)[{n}]) {{ dft{n}(re, im); }} }};")
+    parts.append("template <> struct Dft<1> { template <class V> static B2S_HD void run(V (&)[1], V (&)[1]) {} };")
     parts.append("}  // namespace b2s")
     OUT.parent.mkdir(parents=True, exist_ok=True)
     OUT.write_text("\n".join(parts) + "\n")
