@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...);          // defined in b2s_abi.cu (thread-
 inline int fail(int code, const char* what) { set_error("%s", what); return code; }
 
 extern std::atomic<unsigned long long> g_kernel_launches;
+extern std::atomic<int> g_fused_path;          // b2s_abi.cu; kernel family of the fused plan sizes (b2s_set_fused_path)
 extern std::atomic<int> g_sm_reserve;          // b2s_abi.cu; SMs the persistent kernels leave free (b2s_set_sm_reserve)   // b2s_abi.cu; kernels launched through this library
 
 inline int check_launch(const char* what, int n_kernels = 1) {
@@ -45,7 +46,6 @@ int generic_fft2(const float* in, float* out, int64_t n_images, int h, int w, in
 
 // strip-streamed fused kernels (b2s_strip.cu), h == w in {200, 256}.  `*unavailable` = 1 (and B2S_OK) when the
 // launch could not be made (stream capturing before the workspace exists): the caller uses the on-chip kernels.
-int use_strip();
 int strip_fft2c(int h, const float* in, float* out, int64_t n, int inverse, float scale, cudaStream_t st, int* unavailable);
 int strip_expand(int h, const float* image, const float* sens, float* kspace, const float* ref, const uint8_t* mask,
                  const float* v, int mode, int t, int c, int64_t n, float scale, cudaStream_t st, int* unavailable);

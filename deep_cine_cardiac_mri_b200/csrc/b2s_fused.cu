@@ -5,141 +5,104 @@
 #include "b2s_common.cuh"
 #include "sense_functors.cuh"
 #include "fft2_kernel.cuh"
-#include "fft2_whole.cuh"
+#include "fft2_whole.cuh"     // (parking-lot types; the scalar whole-image kernel itself is experimental)
 #include "fft2_packed.cuh"
 
 using namespace b2s;
 
+// Which kernel family serves the fused plan sizes (b2s_set_fused_path, include/b200sense.h):
+//   0 auto (default)  1 strip-streamed (experimental builds)  2 half/quarter-split only  3 packed whole-image wherever it exists
+
 namespace {
 
 typedef Plan<200, 200, 256, 1, 2> P200H;   // half split: 8 warps x 255 registers, 1 CTA/SM
-typedef Plan<200, 200, 128, 1, 4> P200Q;   // quarter split: 2 CTAs x 4 warps per SM
 typedef Plan<256, 256, 256, 1, 4> P256;    // quarter split, 1 CTA/SM
 typedef Plan<200, 200, 256, 2, 2, 1> P200W; // half split, 128-bit Phase A loads (two columns per thread)
 typedef Plan<256, 256, 256, 2, 4, 1> P256W; // quarter split, 128-bit Phase A loads
-constexpr int W256_PLAIN = 0;
+typedef PackPlan200<256> PK200;             // packed whole-image kernel (fft2_packed.cuh)
+#ifdef B2S_EXPERIMENTS
+typedef Plan<200, 200, 128, 1, 4> P200Q;   // quarter split: 2 CTAs x 4 warps per SM
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
-static int use_whole() { return env_int("B2S_WHOLE", 1); }   // 200 x 200: whole-image kernel with the TMEM parking lot
-static int use_packed() { return env_int("B2S_PACKED", 1); } // ... with packed two-transform arithmetic (fft2_packed.cuh)
-#define B2S_WHOLE(PRO, EPI, QD, TT, CARRY, REV, pro, epi, s, n, st) \
-  (use_packed() ? launch_whole<P, PRO, EPI, QD, TT, CARRY, REV, true>(pro, epi, s, n, st) : launch_whole<P, PRO, EPI, QD, TT, CARRY, REV, false>(pro, epi, s, n, st))               // auto choice of P256W for fft2c / sens_reduce (sens_expand: always)
+#endif
 
-// B2S_WIDE: unset/-1 = auto (128-bit Phase A only where it measured faster: the two-stream sens_expand
-// without the DC epilogue, 148 vs 162 us), 0 = never, 1 = always.
-static int use_wide(int auto_on = 0) {
-  static int q = -2;
-  if (q == -2) { const char* e = getenv("B2S_WIDE"); q = e ? atoi(e) : -1; }
-  return q < 0 ? auto_on : q;
+struct DeviceInfo { int sms; };
+static int device_info(DeviceInfo& d) {
+  int dev = 0;
+  B2S_CUDA(cudaGetDevice(&dev));
+  static std::atomic<int> sm_count[64];       // immutable per-device facts (zero-initialised statics)
+  if (dev < 0 || dev >= 64) return fail(B2S_EUNSUPPORTED, "device index >= 64");
+  if (!sm_count[dev].load()) { int n = 0; B2S_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); sm_count[dev].store(n); }
+  d.sms = sm_count[dev].load();
+  return B2S_OK;
 }
+static int grid_slots(const DeviceInfo& d) { const int r = g_sm_reserve.load(); return d.sms - r > 0 ? d.sms - r : 1; }   // see b2s_set_sm_reserve
 
-// B2S_SPLIT=4: quarter split with two 128-thread CTAs per SM (measured slower: 431 vs 330 us per DC step)
-static int use_quarter() {
-  static int q = -1;
-  if (q < 0) { const char* e = getenv("B2S_SPLIT"); q = (e && atoi(e) == 4) ? 1 : 0; }
-  return q;
+template <class K> static int allow_smem(K kern, int bytes) {
+  int dev = 0;
+  B2S_CUDA(cudaGetDevice(&dev));
+  static std::atomic<bool> configured[64];    // per kernel instantiation and device; setting the attribute twice is harmless
+  if (!configured[dev & 63].load()) {
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    configured[dev & 63].store(true);
+  }
+  return B2S_OK;
 }
 
 // REVERSE: the kernel walks the images last-to-first (sens_reduce: it usually follows the kernel that wrote them, and
-// the end of a 192 MB stream is what is still in the 126 MB L2)
+// the end of a 192 MB stream is what is still in the 126 MB L2).  `first_image`: images before it are skipped (they
+// were handled by the whole-image kernel; with REVERSE the LAST first_image images are the ones skipped).
 template <class P, class Pro, class Epi, bool CARRY = false, bool REVERSE = false>
 int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st, int64_t first_image = 0) {
   if (n_images <= first_image) return B2S_OK;
   if (P::FOLD * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
   auto kern = fft2_half_kernel<P, Pro, Epi, CARRY, REVERSE>;
-  int dev = 0, sms = 0;
-  B2S_CUDA(cudaGetDevice(&dev));
-  static std::atomic<int> sm_count[64];       // immutable per-device facts (zero-initialised statics)
-  static std::atomic<bool> configured[64];    // per instantiation and device; setting the attribute twice is harmless
-  if (dev < 0 || dev >= 64) return fail(B2S_EUNSUPPORTED, "device index >= 64");
-  if (!sm_count[dev].load()) { int n = 0; B2S_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); sm_count[dev].store(n); }
-  sms = sm_count[dev].load();
-  if (!configured[dev].load()) {
-    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<P>::SMEM_BYTES));
-    configured[dev].store(true);
-  }
-  const int n_items = (int)(P::FOLD * n_images), item0 = (int)(P::FOLD * first_image);   // (reverse order: the LAST first_image images are skipped)
-  const int slots = (sms - g_sm_reserve.load() > 0 ? sms - g_sm_reserve.load() : 1) * P::CTAS;   // see b2s_set_sm_reserve
+  DeviceInfo d;
+  if (int rc = device_info(d)) return rc;
+  if (int rc = allow_smem(kern, Derived<P>::SMEM_BYTES)) return rc;
+  const int n_items = (int)(P::FOLD * n_images), item0 = (int)(P::FOLD * first_image);
+  const int slots = grid_slots(d) * P::CTAS;
   const unsigned grid = (unsigned)(n_items - item0 < slots ? n_items - item0 : slots);   // persistent: P::CTAS CTAs per SM
   kern<<<grid, P::NT, Derived<P>::SMEM_BYTES, st>>>(pro, epi, scale, n_items, item0);
   return check_launch("fft2_half_kernel");
 }
 
-// Whole-image kernel (fft2_whole.cuh, TMEM parking lot) on as many images as fill whole rounds of the persistent
-// grid; a remainder that fits one round of half items (2 * rem <= CTAs) goes through the half-split kernel behind it
-// (a ragged last round of whole images would idle most SMs for a full image time).
-template <class P, class Pro, class Epi, int QD, int TT, bool CARRY = false, bool REVERSE = false, bool PACKED = false, class TailEpi = Epi>
-int launch_whole(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st, const TailEpi* tail_epi = nullptr) {
+// Packed whole-image kernel (fft2_packed.cuh: one image per CTA, second half parked in tensor memory, two transforms
+// per thread in packed fp32) on as many images as fill whole rounds of the persistent grid; a remainder that fits one
+// round of half items (2 * rem <= CTAs) goes through the half-split kernel behind it with the epilogue `tail_epi` (a
+// ragged last round of whole images would idle most SMs for a full image time).
+template <class P, class Pro, class Epi, int QD, int TT, bool CARRY, bool REVERSE, class TailEpi>
+int launch_packed(const Pro& pro, const Epi& epi, const TailEpi& tail_epi, float scale, int64_t n_images, cudaStream_t st) {
   if (n_images <= 0) return B2S_OK;
   if (2 * n_images > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
-  typedef PackPlan200<256> PP;
-  static_assert(!PACKED || (P::H == 200 && P::W == 200), "packed kernel: 200 x 200 only");
-  constexpr int SMEM = PACKED ? PkSmem<PP, Epi>::BYTES : WholeSmem<P>::BYTES;
-  void (*kern)(const Pro, const Epi, const float, const int, const int, const int, const int);
-  if constexpr (PACKED) kern = fft2_packed_kernel<PP, Pro, Epi, QD, TT, CARRY, REVERSE>;
-  else kern = fft2_whole_kernel<P, Pro, Epi, QD, TT, CARRY, REVERSE>;
-  int dev = 0;
-  B2S_CUDA(cudaGetDevice(&dev));
-  static std::atomic<int> sm_count[64];
-  static std::atomic<bool> configured[64];
-  if (dev < 0 || dev >= 64) return fail(B2S_EUNSUPPORTED, "device index >= 64");
-  if (!sm_count[dev].load()) { int n = 0; B2S_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); sm_count[dev].store(n); }
-  if (!configured[dev].load()) {
-    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured[dev].store(true);
-  }
-  const int sms = sm_count[dev].load();
-  const int slots = sms - g_sm_reserve.load() > 0 ? sms - g_sm_reserve.load() : 1;
+  auto kern = fft2_packed_kernel<PK200, Pro, Epi, QD, TT, CARRY, REVERSE>;
+  constexpr int SMEM = PkSmem<PK200, Epi>::BYTES;
+  DeviceInfo d;
+  if (int rc = device_info(d)) return rc;
+  if (int rc = allow_smem(kern, SMEM)) return rc;
+  const int slots = grid_slots(d);
   int64_t n_whole = n_images;
   const int64_t rem = n_images % slots;
-  if (n_images > slots && rem > 0 && 2 * rem <= slots && env_int("B2S_WHOLE_TAIL", 1)) n_whole = n_images - rem;
+  if (n_images > slots && rem > 0 && 2 * rem <= slots) n_whole = n_images - rem;
   const unsigned grid = (unsigned)(n_whole < slots ? n_whole : slots);
-  kern<<<grid, P::NT, SMEM, st>>>(pro, epi, scale, (int)n_whole, (int)n_images, env_int("B2S_AHEAD", 1), env_int("B2S_CDUAL", 0));
-  int rc = check_launch("fft2_whole_kernel");
+  kern<<<grid, PK200::NT, SMEM, st>>>(pro, epi, scale, (int)n_whole, (int)n_images, 1, 0);
+  const int rc = check_launch("fft2_packed_kernel");
   if (rc || n_whole == n_images) return rc;
-  if constexpr (std::is_same<TailEpi, Epi>::value) return launch_fused<P, Pro, Epi, CARRY, REVERSE>(pro, epi, scale, n_images, st, n_whole);
-  else return launch_fused<P, Pro, TailEpi, CARRY, REVERSE>(pro, *tail_epi, scale, n_images, st, n_whole);
+  return launch_fused<P, Pro, TailEpi, CARRY, REVERSE>(pro, tail_epi, scale, n_images, st, n_whole);
 }
 
-// Paired variant: clusters of two CTAs (one image per cluster at a time), see PhaseA2.
-template <class P, class Pro, class Epi, bool CARRY = false>
-int launch_pair(const Pro& pro, const Epi& epi, float scale, int64_t n_images, cudaStream_t st) {
-  if (n_images <= 0) return B2S_OK;
-  if (n_images > 0x3fffffffLL) return fail(B2S_EUNSUPPORTED, "too many images for one launch");
-  auto kern = fft2_pair_kernel<P, Pro, Epi, CARRY>;
-  int dev = 0;
-  B2S_CUDA(cudaGetDevice(&dev));
-  static std::atomic<int> sm_count[64];
-  static std::atomic<bool> configured[64];
-  if (dev < 0 || dev >= 64) return fail(B2S_EUNSUPPORTED, "device index >= 64");
-  if (!sm_count[dev].load()) { int n = 0; B2S_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)); sm_count[dev].store(n); }
-  if (!configured[dev].load()) {
-    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Derived<P>::SMEM_BYTES));
-    configured[dev].store(true);
-  }
-  const long long max_pairs = sm_count[dev].load() / 2;
-  const unsigned pairs = (unsigned)(n_images < max_pairs ? n_images : max_pairs);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(P::NT); cfg.dynamicSmemBytes = Derived<P>::SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  const int n = (int)n_images;
-  B2S_CUDA(cudaLaunchKernelEx(&cfg, kern, pro, epi, scale, n));
-  return check_launch("fft2_pair_kernel");
+// Measured cost model (B200, microseconds per round of the 148-CTA persistent grid, profiles/r2_analysis.md): the
+// packed whole-image kernel processes an image in less SM time, but its work items are twice as coarse, so a launch
+// whose image count is not a multiple of the grid pays a tail (remainder through the half-split kernel behind it).
+struct KernelCost { float whole_round, half_round, tail; };
+static bool packed_is_faster(int64_t n, int slots, const KernelCost& k) {
+  const int path = g_fused_path.load();
+  if (path == 2) return false;
+  if (path == 3) return true;
+  const int64_t rem = n % slots;
+  const float whole = (float)(n / slots) * k.whole_round + (rem == 0 ? 0.f : (n > slots && 2 * rem <= slots ? k.tail : k.whole_round));
+  const float half = (float)((2 * n + slots - 1) / slots) * k.half_round;
+  return whole < half;
 }
-
-// B2S_PAIR: 1 = use the paired (2-CTA cluster, DSMEM) kernel, otherwise not.  It halves the L2 -> SM ingest
-// of Phase A and measured 152 vs 162 us for the plain sens_expand, but the 128-bit Phase A (B2S_WIDE) is
-// faster still (148 us) and it loses for every other operator, so nothing selects it by default.
-static int use_pair(int auto_on = 0) {
-  static int p = -2;
-  if (p == -2) { const char* e = getenv("B2S_PAIR"); p = e ? atoi(e) : -1; }
-  return p < 0 ? auto_on : p;
-}
-
-// B2S_DCFIX=0: fused predicated soft-DC epilogue (round 1) instead of the row fix-up (EpiDCFix)
-static int use_dcfix() { return env_int("B2S_DCFIX", 0); }
 
 }  // namespace
 
@@ -149,17 +112,15 @@ int plan_fft2c(const float* in, float* out, int64_t n_images, int inverse, float
   constexpr int H = P::H, W = P::W;
   const long long hw = (long long)H * W;
   const float s = scale * centre_sign<P>();
+  // (the packed whole-image kernel ties with the half split for the plain transform and for sens_reduce at full rounds
+  // and loses with a remainder - profiles/r2_analysis.md - so they stay on the half split)
   if (inverse) {
     ProPlain<H, W, true> pro{(const cfloat*)in, hw};
     EpiPlain<H, W, true> epi{(cfloat*)out, hw};
-    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) { typedef ProPlain<H, W, true> PR; typedef EpiPlain<H, W, true> EP; return B2S_WHOLE(PR, EP, 5, 1, true, false, pro, epi, s, n_images, st); } }
-    if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st); }
     return launch_fused<P, ProPlain<H, W, true>, EpiPlain<H, W, true>, true>(pro, epi, s, n_images, st);
   }
   ProPlain<H, W, false> pro{(const cfloat*)in, hw};
   EpiPlain<H, W, false> epi{(cfloat*)out, hw};
-  if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) { typedef ProPlain<H, W, false> PR; typedef EpiPlain<H, W, false> EP; return B2S_WHOLE(PR, EP, 5, 1, true, false, pro, epi, s, n_images, st); } }
-  if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st); }
   return launch_fused<P, ProPlain<H, W, false>, EpiPlain<H, W, false>, true>(pro, epi, s, n_images, st);
 }
 
@@ -173,25 +134,31 @@ int plan_expand(const float* image, const float* sens, float* kspace, const floa
 #define B2S_RUN(M)                                                                    \
   {                                                                                   \
     EpiKspace<H, W, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};      \
-    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) { typedef ProExpand<H, W> PR; typedef EpiKspace<H, W, M> EP; return B2S_WHOLE(PR, EP, 2, 2, false, false, pro, epi, s, n, st); } } \
-    if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
     return launch_fused<P>(pro, epi, s, n, st);                                       \
   }
-  if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) {
-    // soft DC on the packed whole-image kernel with the reference rows staged in shared memory by the bulk-copy engine
-    if (mode == 2 && use_whole() && use_packed() && env_int("B2S_DCSTAGE", 1) && ((uintptr_t)ref & 15) == 0) {
-      EpiDCStage<H, W> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};
-      EpiKspace<H, W, 2> tail{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};
-      return launch_whole<P, ProExpand<H, W>, EpiDCStage<H, W>, 2, 2, false, false, true, EpiKspace<H, W, 2>>(pro, epi, s, n, st, &tail);
-    }
-  }
-  if (mode == 2 && use_dcfix() && (((uintptr_t)kspace | (uintptr_t)ref) & 15) == 0) {
-    // soft DC as a row fix-up behind the plain transform (EpiDCFix); needs 16-byte aligned k-space rows
-    EpiDCFix<H, W> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw, env_int("B2S_DCFIX_PF", 3)};
-    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) { typedef ProExpand<H, W> PR; typedef EpiDCFix<H, W> EP; return B2S_WHOLE(PR, EP, 2, 2, false, false, pro, epi, s, n, st); } }
-    return launch_fused<P>(pro, epi, s, n, st);
-  }
   switch (mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) case 2: B2S_RUN(2) default: B2S_RUN(3) }
+#undef B2S_RUN
+}
+
+// sens_expand at 200 x 200 on the packed whole-image kernel (remainder images: half split, same epilogue semantics)
+static int packed_expand(const float* image, const float* sens, float* kspace, const float* ref, const uint8_t* mask,
+                         const float* v, int mode, int t, int c, int64_t n, float scale, cudaStream_t st) {
+  constexpr int H = 200, W = 200;
+  const long long hw = (long long)H * W;
+  const float s = scale * centre_sign<P200H>();
+  typedef ProExpand<H, W> PR;
+  PR pro{(const cfloat*)image, (const cfloat*)sens, t, c, hw};
+#define B2S_RUN(M)                                                                    \
+  {                                                                                   \
+    EpiKspace<H, W, M> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};      \
+    return launch_packed<P200H, PR, EpiKspace<H, W, M>, 2, 2, false, false>(pro, epi, epi, s, n, st); \
+  }
+  if (mode == 2) {        // soft DC: reference rows staged in shared memory (EpiDCStage); tail images: fused epilogue
+    EpiDCStage<H, W> epi{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};
+    EpiKspace<H, W, 2> tail{(cfloat*)kspace, (const cfloat*)ref, mask, v, c, hw};
+    return launch_packed<P200H, PR, EpiDCStage<H, W>, 2, 2, false, false>(pro, epi, tail, s, n, st);
+  }
+  switch (mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) default: B2S_RUN(3) }
 #undef B2S_RUN
 }
 
@@ -208,8 +175,6 @@ int plan_reduce(const float* kspace, const float* mult, float* out, const uint8_
 #define B2S_RUN(M)                                                      \
   {                                                                     \
     ProKspace<H, W, M> pro{(const cfloat*)kspace, mask, v, c, hw};      \
-    if constexpr (P::H == 200 && P::FOLD == 2 && P::NC == 1) { if (use_whole()) { typedef ProKspace<H, W, M> PR; typedef EpiReduce<H, W> EP; return B2S_WHOLE(PR, EP, 5, 1, false, true, pro, epi, s, n, st); } } \
-    if constexpr (P::FOLD == 2 && P::NC == 1) { if (use_pair()) return launch_pair<P>(pro, epi, s, n, st); } \
     return launch_fused<P, ProKspace<H, W, M>, EpiReduce<H, W>, false, true>(pro, epi, s, n, st); \
   }
   switch (weight_mode) { case 0: B2S_RUN(0) case 1: B2S_RUN(1) default: B2S_RUN(2) }
@@ -236,6 +201,16 @@ int plan_ifft_weighted(const float* kspace, float* y, const uint8_t* mask, const
 
 static inline int plan_id(int h, int w) { return (h == 200 && w == 200) ? 1 : (h == 256 && w == 256) ? 2 : 0; }
 
+static inline bool aligned16(const void* a, const void* b = nullptr, const void* c2 = nullptr) {
+  return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c2) & 15) == 0;
+}
+
+#ifdef B2S_EXPERIMENTS
+namespace {
+#include "b2s_fused_experiments.inc"
+}
+#endif
+
 extern "C" int b2s_has_fused_plan(int h, int w) { return plan_id(h, w) ? 1 : 0; }
 
 extern "C" size_t b2s_scratch_bytes(int b, int t, int c, int h, int w) {
@@ -250,14 +225,12 @@ extern "C" int b2s_fft2c(const float* in, float* out, int64_t n_images, int h, i
   if (!in || !out) return fail(B2S_EINVAL, "b2s_fft2c: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = norm_scale(h, w, inverse, norm);
-  if (plan_id(h, w) && use_strip()) {
-    int un = 0;
-    const int rc = strip_fft2c(h, in, out, n_images, inverse, scale, st, &un);
-    if (rc || !un) return rc;
-  }
+#ifdef B2S_EXPERIMENTS
+  { int rc = 0; if (experimental_fft2c(in, out, n_images, h, w, inverse, scale, st, &rc)) return rc; }
+#endif
   switch (plan_id(h, w)) {
-    case 1: return use_wide() ? plan_fft2c<P200W>(in, out, n_images, inverse, scale, st) : use_quarter() ? plan_fft2c<P200Q>(in, out, n_images, inverse, scale, st) : plan_fft2c<P200H>(in, out, n_images, inverse, scale, st);
-    case 2: return use_wide(W256_PLAIN) ? plan_fft2c<P256W>(in, out, n_images, inverse, scale, st) : plan_fft2c<P256>(in, out, n_images, inverse, scale, st);
+    case 1: return plan_fft2c<P200H>(in, out, n_images, inverse, scale, st);
+    case 2: return plan_fft2c<P256>(in, out, n_images, inverse, scale, st);
     default: return generic_fft2(in, out, n_images, h, w, inverse, scale, st);
   }
 }
@@ -275,18 +248,24 @@ extern "C" int b2s_sens_expand(const float* image, const float* sens, float* ksp
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = (int64_t)b * t * c;
   const float scale = norm_scale(h, w, 0, norm);
-  if (plan_id(h, w) && use_strip()) {
-    int un = 0;
-    const int rc = strip_expand(h, image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st, &un);
-    if (rc || !un) return rc;
-  }
+#ifdef B2S_EXPERIMENTS
+  { int rc = 0; if (experimental_expand(image, sens, kspace, ref, mask, v, mode, t, c, n, h, w, scale, st, &rc)) return rc; }
+#endif
+  // 128-bit Phase A loads need 16-byte aligned rows (a tensor view at an odd complex offset is only 8-byte aligned)
+  const bool wide_ok = aligned16(image, sens);
   switch (plan_id(h, w)) {
-    case 1: return (!use_whole() && ((mode == 2 && use_dcfix()) ? env_int("B2S_DCFIX_WIDE", 0) : use_wide(mode != 2)))
-                 ? plan_expand<P200W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
-                 : use_quarter() ? plan_expand<P200Q>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
-                                 : plan_expand<P200H>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
-    case 2: return use_wide(1) ? plan_expand<P256W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
-                               : plan_expand<P256>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
+    case 1: {
+      DeviceInfo d;
+      if (int rc = device_info(d)) return rc;
+      // per round of the persistent grid, microseconds: {packed whole image, half item, tail launch}
+      const KernelCost cost = (mode == 2) ? KernelCost{39.5f, 20.8f, 28.f} : KernelCost{27.8f, 17.0f, 22.f};
+      if ((mode != 2 || aligned16(ref)) && packed_is_faster(n, grid_slots(d), cost))
+        return packed_expand(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
+      return (wide_ok && mode != 2) ? plan_expand<P200W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
+                                    : plan_expand<P200H>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
+    }
+    case 2: return wide_ok ? plan_expand<P256W>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st)
+                           : plan_expand<P256>(image, sens, kspace, ref, mask, v, mode, t, c, n, scale, st);
     default: break;
   }
   // generic sizes: S*x -> kspace, FFT in place, epilogue in place
@@ -318,12 +297,6 @@ extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* ou
     const size_t need = (size_t)n * hw * 2 * sizeof(float);
     if (!scratch || scratch_bytes < need) return fail(B2S_EINVAL, "b2s_sens_reduce: deterministic mode needs b*t*c*h*w*8 scratch bytes");
     float* y = (float*)scratch;
-    if (use_strip()) {
-      int un = 0;
-      const int rcs = strip_ifft_weighted(h, kspace, y, mask, v, weight_mode, c, n, scale, st, &un);
-      if (rcs) return rcs;
-      if (!un) return launch_coil_reduce(y, mult, out, over_frames, b, t, c, hw, st);
-    }
     const int rc = plan_id(h, w) == 2 ? plan_ifft_weighted<P256>(kspace, y, mask, v, weight_mode, c, n, scale, st)
                                       : plan_ifft_weighted<P200H>(kspace, y, mask, v, weight_mode, c, n, scale, st);
     if (rc) return rc;
@@ -332,16 +305,11 @@ extern "C" int b2s_sens_reduce(const float* kspace, const float* mult, float* ou
   if (plan_id(h, w)) {
     B2S_CUDA(cudaMemsetAsync(out, 0, (size_t)out_images * hw * 2 * sizeof(float), st));
     if (n == 0) return B2S_OK;
-    if (use_strip()) {
-      int un = 0;
-      const int rcs = strip_reduce(h, kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st, &un);
-      if (rcs || !un) return rcs;
-    }
-    if (plan_id(h, w) == 2) return use_wide(W256_PLAIN) ? plan_reduce<P256W>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
-                                                       : plan_reduce<P256>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
-    return use_wide() ? plan_reduce<P200W>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
-         : use_quarter() ? plan_reduce<P200Q>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st)
-                         : plan_reduce<P200H>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
+#ifdef B2S_EXPERIMENTS
+    { int rc = 0; if (experimental_reduce(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, h, w, scale, st, &rc)) return rc; }
+#endif
+    if (plan_id(h, w) == 2) return plan_reduce<P256>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
+    return plan_reduce<P200H>(kspace, mult, out, mask, v, weight_mode, over_frames, t, c, n, scale, st);
   }
   // generic sizes: (row weight) -> IFFT into scratch -> conj-multiply + reduce
   const size_t need = (size_t)n * hw * 2 * sizeof(float);

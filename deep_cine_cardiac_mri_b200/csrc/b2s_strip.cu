@@ -128,16 +128,7 @@ template <int N> float strip_sign() { return ((N / 2) & 1) ? -1.f : 1.f; }
 
 namespace b2s {
 
-// Which fused implementation serves the plan sizes: 0 = on-chip half/quarter-split kernels (fft2_core.cuh),
-// 1 = strip-streamed kernels (this file).  b2s_set_fused_path() overrides the environment (B2S_PATH=strip|half);
-// the default is the on-chip path, which measured faster on B200 for every operator at 200 x 200
-// (profiles/r1_strip_experiment.md).
-static std::atomic<int> g_path{-1};
-int use_strip() {
-  int v = g_path.load();
-  if (v < 0) { const char* e = getenv("B2S_PATH"); v = (e && e[0] == 's') ? 1 : 0; g_path.store(v); }
-  return v;
-}
+// (selected by b2s_set_fused_path(1) / B2S_STRIP=1 in experimental builds: b2s_fused_experiments.inc)
 
 template <int H, int W>
 int strip_fft2c_t(const float* in, float* out, int64_t n, int inverse, float scale, cudaStream_t st, int* un) {
@@ -207,12 +198,6 @@ int strip_ifft_weighted(int h, const float* kspace, float* y, const uint8_t* mas
 }
 
 }  // namespace b2s
-
-extern "C" int b2s_set_fused_path(int path) {
-  if (path < -1 || path > 1) return fail(B2S_EINVAL, "b2s_set_fused_path: path must be -1 (environment), 0 (on-chip) or 1 (strip)");
-  g_path.store(path);
-  return B2S_OK;
-}
 
 // 0 = no dependency wait ever timed out on any workspace of this process (synchronises the device)
 extern "C" int b2s_debug_strip_status(void) {

@@ -91,9 +91,12 @@ def deterministic() -> bool:
 
 
 def set_fused_path(path) -> None:
-    """Implementation behind the fused plan sizes (200x200, 256x256): "onchip" (half/quarter-split kernels, default),
-    "strip" (two passes through an L2-resident scratch ring) or None (environment: B2S_PATH=strip|half)."""
-    code = {None: -1, "onchip": 0, "half": 0, "strip": 1}[path]
+    """Kernel family behind the fused plan sizes (a test / measurement knob; process-wide):
+    None / "auto"  the library's measured cost model chooses per launch (default),
+    "half"         half-split (200x200) / quarter-split (256x256) kernels only,
+    "packed"       the packed whole-image kernel (second half parked in tensor memory) wherever it exists,
+    "strip"        strip-streamed kernels - only in libraries built with `make EXPERIMENTS=1` (ValueError otherwise)."""
+    code = {None: 0, "auto": 0, "strip": 1, "half": 2, "onchip": 2, "packed": 3}[path]
     _lib.check(_lib.lib().b2s_set_fused_path(code), "set_fused_path")
 
 

@@ -60,13 +60,17 @@ unsigned long long b2s_launch_count(int reset);
  * b2s_upload_rows runs as `n_sms` 1024-thread CTAs on them - the sparse upload of the next batch then overlaps the
  * compute of the current one instead of queueing behind its statically strided grids.  0 (default) = use every SM. */
 int b2s_set_sm_reserve(int n_sms);
-/* Diagnostic of the strip-streamed kernels (csrc/strip_core.cuh): synchronises the current device and returns 0 when
- * no inter-CTA dependency wait ever timed out on it (non-zero = results of that launch are invalid; -1 = CUDA error). */
+/* Diagnostic of the strip-streamed kernels (experimental builds, `make EXPERIMENTS=1`): synchronises the current device
+ * and returns 0 when no inter-CTA dependency wait ever timed out on it (always 0 in product builds). */
 int b2s_debug_strip_status(void);
-/* Selects the implementation behind the fused plan sizes (200x200, 256x256) of b2s_fft2c / b2s_sens_expand /
- * b2s_sens_reduce: 0 = on-chip half/quarter-split kernels (default), 1 = strip-streamed kernels (two passes through
- * an L2-resident scratch ring, csrc/strip_core.cuh), -1 = re-read the environment (B2S_PATH=strip|half).  Both compute
- * the same operators (same parity tests); process-wide. */
+/* Kernel family behind the fused plan sizes (200x200, 256x256) of b2s_fft2c / b2s_sens_expand / b2s_sens_reduce - a test
+ * and measurement knob, process-wide, every family computes the same operators (same parity tests):
+ *   0 or -1  automatic (default): per launch, the measured cost model of csrc/b2s_fused.cu picks between
+ *   2        the half-split (200x200) / quarter-split (256x256) on-chip kernels (csrc/fft2_core.cuh) and
+ *   3        the packed whole-image kernel (200x200 sens_expand: one image per CTA, second half of the intermediate
+ *            parked in tensor memory, two transforms per thread in packed fp32 - csrc/fft2_packed.cuh);
+ *   1        strip-streamed kernels (two passes through an L2-resident ring, csrc/strip_core.cuh) - experimental builds
+ *            only, B2S_EUNSUPPORTED otherwise. */
 int b2s_set_fused_path(int path);
 /* 1 if (h,w) runs on the fused single-pass kernels, 0 if on the generic two-pass ones */
 int b2s_has_fused_plan(int h, int w);

@@ -48,13 +48,15 @@ def test_abi_option_entry_points_validate_their_arguments():
     """b2s_set_fused_path / b2s_set_sm_reserve are host-only switches: callable without a GPU, bad values are refused."""
     from deep_cine_cardiac_mri_b200 import _lib, ops
     lib = _lib.lib()
-    assert lib.b2s_set_fused_path(2) == 1 and b"b2s_set_fused_path" in lib.b2s_last_error()
-    assert lib.b2s_set_fused_path(1) == 0 and lib.b2s_set_fused_path(0) == 0 and lib.b2s_set_fused_path(-1) == 0
+    assert lib.b2s_set_fused_path(7) == 1 and b"b2s_set_fused_path" in lib.b2s_last_error()
+    assert lib.b2s_set_fused_path(2) == 0 and lib.b2s_set_fused_path(3) == 0 and lib.b2s_set_fused_path(0) == 0 and lib.b2s_set_fused_path(-1) == 0
+    assert lib.b2s_set_fused_path(1) in (0, 2)            # strip-streamed kernels: experimental builds only (2 = EUNSUPPORTED)
+    lib.b2s_set_fused_path(0)
     assert lib.b2s_set_sm_reserve(-1) == 1 and lib.b2s_set_sm_reserve(65) == 1
     assert lib.b2s_set_sm_reserve(4) == 0 and lib.b2s_set_sm_reserve(0) == 0
     with pytest.raises(KeyError):
         ops.set_fused_path("tensor-cores")
-    ops.set_fused_path("strip"); ops.set_fused_path(None)
+    ops.set_fused_path("half"); ops.set_fused_path("packed"); ops.set_fused_path(None)
     with pytest.raises(ValueError):
         ops.upload_masked_kspace(__import__("torch").zeros(1, 1, 1, 4, 4, 2), __import__("torch").zeros(1, 1, 4, dtype=__import__("torch").uint8))
 
@@ -285,8 +287,8 @@ def _fake_reference(tmp_path):
         ["fft1c", "ifft1c", "fft2c", "ifft2c", "fftshift", "ifftshift", "roll", "complex_mul", "complex_conj",
          "complex_abs", "complex_abs_sq", "rss", "rss_complex", "pad_for_mwcnn", "unpad_from_mwcnn"]))
     body = {"varnet": ["VarNetBlock", "VarNet", "SensitivityModel"], "cinenet": ["CineNetBlock", "CineNet"],
-            "xpdnet": ["ForwardOperator", "BackwardOperator", "SensitivityModel", "XPDNetBlock"],
-            "recurrent_varnet": ["VarNet_RNN"], "recurrent_cinenet": ["CineNet_RNN"]}
+            "xpdnet": ["ForwardOperator", "BackwardOperator", "SensitivityModel", "XPDNetBlock", "XPDNet"],
+            "recurrent_varnet": ["VarNet_RNN"], "recurrent_cinenet": ["CineNet_RNN"], "recurrent_xpdnet": ["XPDNet_RNN"]}
     for mod, classes in body.items():
         (pkg / "models" / f"{mod}.py").write_text("".join(
             f"class {c}:\n    def forward(self, *a):\n        return 'reference'\n    def sens_expand(self, *a):\n        return 'reference'\n" for c in classes))
@@ -312,6 +314,10 @@ def test_patch_and_unpatch_reference(tmp_path, monkeypatch):
         assert V.VarNetBlock.sens_expand is blocks.sens_expand
         assert X.ForwardOperator.forward is blocks.forward_operator_forward
         assert hasattr(X.XPDNetBlock, "xfyf_transform")
+        assert X.XPDNetBlock.k_domain_correction is blocks.xpdnet_k_domain_correction
+        assert X.XPDNetBlock.i_domain_correction is blocks.xpdnet_i_domain_correction
+        import reconstruction.models.recurrent_xpdnet as RX
+        assert RX.XPDNet_RNN.update_image_buffer is blocks.xpdnet_update_image_buffer
         import reconstruction.utils.losses as L
         assert L.SSIMLoss.forward is patch._ssim_loss_forward
         assert patch.is_patched()

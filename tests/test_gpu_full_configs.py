@@ -7,8 +7,6 @@
 for every kernel family that can serve the size: the persistent loops, image strides and the tail hand-over between
 the whole-image and the half-split kernel only show at these image counts (600 / 500 / 960 coil images per launch).
 The numpy fp64 oracle is the arbiter; tolerance 1e-5 of max|ref| (north_star)."""
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -19,8 +17,7 @@ from oracle import sense_oracle as O
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
 CONFIGS = {"A": (4, 15, 10, 200, 200), "B": (1, 25, 20, 200, 200), "C": (1, 30, 32, 256, 256)}
-# environment switches of csrc/b2s_fused.cu (read at every launch)
-FAMILIES = {"packed": {}, "whole": {"B2S_PACKED": "0"}, "half": {"B2S_WHOLE": "0"}, "half_fused_dc": {"B2S_WHOLE": "0", "B2S_DCFIX": "0"}}
+FAMILIES = ["auto", "half", "packed"]        # ops.set_fused_path
 
 
 def cu(a):
@@ -64,23 +61,17 @@ def case(tag):
 
 @pytest.fixture
 def family(request):
-    env = FAMILIES[request.param]
-    old = {k: os.environ.get(k) for k in ("B2S_PACKED", "B2S_WHOLE", "B2S_DCFIX")}
-    for k in old:
-        os.environ.pop(k, None)
-    os.environ.update(env)
+    from deep_cine_cardiac_mri_b200 import ops
+    ops.set_fused_path(request.param)
     yield request.param
-    for k, val in old.items():
-        os.environ.pop(k, None)
-        if val is not None:
-            os.environ[k] = val
+    ops.set_fused_path(None)
 
 
 @pytest.mark.parametrize("tag", ["A", "B", "C"])
-@pytest.mark.parametrize("family", list(FAMILIES), indirect=True)
+@pytest.mark.parametrize("family", FAMILIES, indirect=True)
 def test_operators_at_full_config(tag, family):
     from deep_cine_cardiac_mri_b200 import ops
-    if tag == "C" and family != "packed":
+    if tag == "C" and family != "auto":
         pytest.skip("256 x 256 has one kernel family (quarter split)")
     cs, v, want = case(tag)
     b, t, c, h, w = CONFIGS[tag]
@@ -95,7 +86,7 @@ def test_operators_at_full_config(tag, family):
     assert rel(ops.sens_reduce(k, sens, mask=mask).unsqueeze(2), want["reduce_mask"]) <= TOL
     assert rel(ops.fft2c(k[:, :2].contiguous(), "ortho"), want["fft2c"]) <= TOL
     assert rel(ops.fft2c(k[:, :2].contiguous(), "ortho", inverse=True), want["ifft2c"]) <= TOL
-    if "normal" in want and family == "packed":
+    if "normal" in want and family == "auto":
         assert rel(ops.normal_op(img.squeeze(2), sens, mask, vd).unsqueeze(2), want["normal"]) <= TOL
     # deterministic coil sum at full size: bit-identical from run to run and equal to the oracle
     ops.set_deterministic(True)

@@ -127,11 +127,15 @@ def make_case(tag):
     return cs, {k: (f64(v) if getattr(v, "dtype", None) == np.float32 and v.ndim else v) for k, v in cs.items()}
 
 
-@pytest.fixture(params=["onchip", "strip"])
+@pytest.fixture(params=["auto", "half", "packed", "strip"])
 def fused_path(request, ops):
-    """Run the test once per implementation of the fused plan sizes: the on-chip half/quarter-split kernels and the
-    strip-streamed kernels (b2s_set_fused_path); the strip run also checks that no dependency wait timed out."""
-    ops.set_fused_path(request.param)
+    """Run the test once per kernel family of the fused plan sizes (b2s_set_fused_path): the library's own choice, the
+    half/quarter-split kernels, the packed whole-image kernel, and - in experimental builds only - the strip-streamed
+    kernels (that run also checks that no dependency wait timed out)."""
+    try:
+        ops.set_fused_path(request.param)
+    except ValueError:
+        pytest.skip("strip-streamed kernels: experimental builds only (make EXPERIMENTS=1)")
     yield request.param
     if request.param == "strip":
         assert ops.strip_status() == 0

