@@ -13,8 +13,12 @@ e2e       the same metric through the public API with HOST (pinned) buffers: H2D
           k-space + mask and D2H of the reconstructed cine inside the timed region.
 roofline  dominant kernel = the fused sens_expand + soft-DC kernel; algorithmic bytes I + S + 2K per
           launch over its CUDA-event duration measured inside the timed region, vs MEASURED_PEAKS.json.
-cpu_baseline / --impl reference   the torch-CPU port of the reference's op chain (oracle/torch_port.py)
-          timed on the host cores on a bounded sample (one slice per step).
+cpu_baseline / --impl reference   the UNMODIFIED reference (baseline/_ref: its own VarNet with the U-Nets swapped for
+          identities, oracle/reference_hot_path.py) timed on the host cores on a bounded sample (one slice per step);
+          the torch-CPU port (oracle/torch_port.py, identical output) only if the reference did not travel.
+extras    dc_step (A^H + A/soft-DC pair: the north_star's "fused SENSE forward+adjoint DC step" roofline),
+          gpu_reference (the unmodified reference on the SAME GPU: eager torch + cuFFT), op_sweep (BASELINE configs[4]),
+          cinenet_hot_path (configs[2]), image_domain_variant.
 Prints exactly ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -33,7 +37,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOAD = "XF-VarNet 12-cascade SENSE/DC hot path, 10-coil 15-frame 200x200 cine slices"
-CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=4, streams=2, upload_sms=4)
+CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=16, streams=2, upload_sms=4)
 for _k, _e in (("upload_sms", "B2S_BENCH_UPLOAD_SMS"), ("streams", "B2S_BENCH_STREAMS"), ("slices_per_gpu_step", "B2S_BENCH_SLICES")):
     if os.environ.get(_e):                          # dev overrides
         CFG[_k] = int(os.environ[_e])
@@ -50,7 +54,9 @@ def load_peaks():
 
 
 def load_traffic():
-    p = ROOT / "profiles" / "r1_traffic.json"
+    p = ROOT / "profiles" / "r2_traffic.json"
+    if not p.exists():
+        p = ROOT / "profiles" / "r1_traffic.json"
     if p.exists():
         try:
             return json.loads(p.read_text()).get("sens_expand_dc_dram_bytes_per_launch")
@@ -118,10 +124,27 @@ def make_inputs(rank: int, n_slices: int):
     return mk, mask
 
 
-def cpu_reference_run(steps: int, warmup: int):
-    """torch-CPU port of the reference path on one slice per step; returns (slices/s, cores, sample)."""
-    import torch
+def reference_model():
+    """(callable(mk, mask) -> cine, kind): the unmodified reference's VarNet with identity regularisers if baseline/_ref
+    travelled ("reference"), else the torch port of the same op chain ("port")."""
+    try:
+        from oracle import load_reference, reference_hot_path
+        if load_reference.available():
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                model = reference_hot_path.reference_varnet_identity(CFG["cascades"], "XF")
+            return model, "reference"
+    except Exception as e:                                       # pragma: no cover
+        print("bench.py: reference not usable, timing the port instead:", repr(e), file=sys.stderr)
     from oracle import torch_port as T
+    return (lambda mk, mask: T.varnet_hot_path(mk, mask, CFG["cascades"], 1.0)), "port"
+
+
+def cpu_reference_run(steps: int, warmup: int):
+    """The reference's CPU path on one slice per step; returns (slices/s, s/step, cores, kind, sample)."""
+    import torch
+    model, kind = reference_model()
     mk, mask = make_inputs(0, 1)
     mk, mask = torch.from_numpy(mk), torch.from_numpy(mask)
     try:                                       # torchrun exports OMP_NUM_THREADS=1; the reference would use every core
@@ -131,24 +154,99 @@ def cpu_reference_run(steps: int, warmup: int):
     cores = torch.get_num_threads()
     with torch.no_grad():
         for _ in range(warmup):
-            T.varnet_hot_path(mk, mask, CFG["cascades"], 1.0)
+            model(mk, mask)
         t0 = time.perf_counter()
         for _ in range(steps):
-            T.varnet_hot_path(mk, mask, CFG["cascades"], 1.0)
+            model(mk, mask)
         dt = time.perf_counter() - t0
-    return steps / dt, dt / steps, cores, f"{steps} x 1 slice (b=1) of the same workload, torch {torch.__version__} CPU, {cores} threads of {os.cpu_count()} cpus"
+    what = "reconstruction.models.VarNet (unmodified reference, regularisers = identity)" if kind == "reference" else "oracle/torch_port.py"
+    return steps / dt, dt / steps, cores, kind, (f"{steps} x 1 slice (b=1) of the same workload through {what}, torch {torch.__version__} CPU, "
+                                                  f"{cores} threads of {os.cpu_count()} cpus")
+
+
+def _median_us(torch, fn, n=12, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for a, b in ev:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return ts[len(ts) // 2] * 1e3
+
+
+def op_sweep(dev, torch, ops):
+    """BASELINE configs[4]: SENSE forward/adjoint DC step over coils x frames x size; b per point such that K ~ 190 MB
+    (> L2 together with the reference k-space).  Per point: microseconds and algorithmic GB/s of the DC step."""
+    peak, _ = load_peaks()
+    rows = []
+    g = torch.Generator(device=dev).manual_seed(7)
+    for hw in (200, 256):
+        for c in (8, 16, 32):
+            for t in (15, 30):
+                b = max(1, round(190e6 / (t * c * hw * hw * 8)))
+                k = torch.randn(b, t, c, hw, hw, 2, device=dev, generator=g)
+                ref = torch.randn(b, t, c, hw, hw, 2, device=dev, generator=g)
+                sens = torch.randn(b, c, hw, hw, 2, device=dev, generator=g)
+                m = (torch.rand(b, t, hw, device=dev, generator=g) < 0.25).to(torch.uint8)
+                v = torch.ones(1, device=dev)
+
+                def dc():
+                    img = ops.raw_sens_reduce(k, sens)
+                    return ops.raw_sens_expand(img, sens, ops.EXPAND_DC, ref, m, v)
+                us = _median_us(torch, dc, n=8)
+                K, I, S = k.numel() * 4, b * t * hw * hw * 8, sens.numel() * 4
+                gbs = (3 * K + 2 * I + 2 * S) / us / 1e3
+                rows.append({"hw": hw, "coils": c, "frames": t, "b": b, "dc_step_us": round(us, 1), "GBps": round(gbs, 1), "frac": round(gbs / peak, 3)})
+                del k, ref, sens
+    return rows
+
+
+def gpu_reference(dev, torch, mk, mask, steps):
+    """The unmodified reference (baseline/_ref) on the same GPU: its VarNet with identity regularisers, b = 1 per call as
+    its SensitivityModel requires, plus the raw torch.fft / eager-op costs of one DC step.  None if it did not travel."""
+    try:
+        model, kind = reference_model()
+        if kind != "reference":
+            return None
+        model = model.to(dev)
+        n = min(mk.shape[0], 4)
+        with torch.no_grad():
+            def fwd():
+                for i in range(n):
+                    model(mk[i:i + 1], mask[i:i + 1])
+            us = _median_us(torch, fwd, n=max(3, min(steps, 6)), warm=1)
+            import reconstruction.utils as U
+            k1 = mk[:1]
+            z = torch.view_as_complex(k1.contiguous())
+            sens = model.sens_net(k1, mask[:1])
+            blk = model.cascades[0]
+            out = {
+                "slices_per_sec": n / (us * 1e-6), "ms_per_slice": us / n * 1e-3, "kind": "reference",
+                "what": "reconstruction.models.VarNet (unmodified, regularisers = identity), eager torch + cuFFT on this GPU, b=1 per call",
+                "per_op_us_b1": {
+                    "raw_torch_fft_fftn": round(_median_us(torch, lambda: torch.fft.fftn(z, dim=(-2, -1), norm="ortho")), 1),
+                    "reference_fft2c": round(_median_us(torch, lambda: U.fft2c(k1)), 1),
+                    "reference_sens_reduce": round(_median_us(torch, lambda: blk.sens_reduce(k1, sens)), 1),
+                    "reference_varnet_block": round(_median_us(torch, lambda: blk(k1, k1, mask[:1], sens)), 1),
+                },
+            }
+        return out
+    except Exception as e:                                       # pragma: no cover
+        return {"error": repr(e)[:300]}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
-    val, sec, cores, sample = cpu_reference_run(steps, warmup)
+    val, sec, cores, kind, sample = cpu_reference_run(steps, warmup)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
            "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, **CFG, "slices_per_step": 1, "note": "bounded sample: one slice per step on host cores"},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), file=_OUT, flush=True)
@@ -323,15 +421,36 @@ def run_ours(args, rank, world, local):
         cine_sec = bdist.max_over_ranks(c0.elapsed_time(c1) * 1e-3, dev)
         n_cine *= NC_SL
 
+        # ---- the north_star's "fused SENSE forward+adjoint DC step": A^H k -> A x fused with the soft-DC blend, timed as a
+        #      pair (CUDA events around both launches) on the step's own tensors; algorithmic bytes 3K + 2I + 2S
+        sens5 = pipeline.sensitivity_maps(mk, mask).squeeze(1).contiguous()
+        m8 = ops._mask_u8(mask, b, t, h)
+        pairs = []
+        for i in range(24):
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            img = ops.raw_sens_reduce(mk, sens5)
+            ops.raw_sens_expand(img, sens5, ops.EXPAND_DC, mk, m8, v)
+            p1.record()
+            pairs.append((p0, p1))
+        torch.cuda.synchronize()
+        pair_ms = sorted(a.elapsed_time(bb) for a, bb in pairs[4:])
+        dc_pair_sec = pair_ms[len(pair_ms) // 2] * 1e-3
+
+        # ---- BASELINE configs[4]: operator sweep (every rank runs it on its own GPU; rank 0 reports its table)
+        sweep = op_sweep(dev, torch, ops) if not args.no_extras else None
+        # ---- the unmodified reference on the SAME GPU (eager torch + cuFFT), rank 0 only
+        gpu_ref = gpu_reference(dev, torch, mk, mask, K) if (rank == 0 and not args.no_extras) else None
+
     if rank != 0:
         return
     peak, peak_src = load_peaks()
     achieved = alg["sens_expand_dc"] / dom_sec / 1e9
-    dc_step_gbs = None
+    dc_alg = 3 * alg["K"] + 2 * alg["I"] + 2 * alg["S"]
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        val, s_per, cores, sample = cpu_reference_run(3, 1)
-        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        val, s_per, cores, kind, sample = cpu_reference_run(3, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
     result = {
         "metric": METRIC, "value": world * nb * K / sec, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -346,11 +465,17 @@ def run_ours(args, rank, world, local):
                 "d2h_bytes_per_step": int(b * t * h * w * 4)},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": load_traffic(), "kernel": "fft2_half_kernel<ProExpand, EpiKspace<DC>> (sens_expand + soft-DC)",
+                     "traffic": load_traffic(), "traffic_source": "ncu dram__bytes of the committed capture (profiles/), not measured in this run",
+                     "kernel": "sens_expand + soft-DC (b2s_sens_expand mode DC: packed whole-image or half-split kernel by the library's cost model)",
                      "algorithmic_bytes_per_launch": alg["sens_expand_dc"], "us_per_launch": dom_sec * 1e6,
                      "launches_timed": len(dom_ms), "peak_source": peak_src,
                      "timed": "separate eager single-stream pass of the same step (kernel alone on the GPU), CUDA events around each launch"},
         "cpu_baseline": cpu,
+        "dc_step": {"bound": "hbm", "achieved": dc_alg / dc_pair_sec / 1e9, "peak": peak, "unit": "GB/s", "frac": dc_alg / dc_pair_sec / 1e9 / peak,
+                    "algorithmic_bytes": dc_alg, "us": dc_pair_sec * 1e6,
+                    "what": "sens_reduce + sens_expand/soft-DC pair (3K + 2I + 2S), median of 20 eager pairs, CUDA events around both launches"},
+        "gpu_reference": gpu_ref,
+        "op_sweep": sweep,
         "cinenet_hot_path": {"value": world * n_cine / cine_sec, "unit": UNIT, "ms_per_slice": cine_sec / n_cine * 1e3,
                              "workload": "CineNet SENSE/CG hot path, 10 iterations x CG 4 (50 normal-operator applications), "
                                          "20-coil 25-frame 200x200, b=1 per call, 4 independent slices on 4 streams in one CUDA graph, regulariser = identity"},
@@ -368,6 +493,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the op sweep and the GPU run of the reference")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -37,16 +37,20 @@ static int device_info(DeviceInfo& d) {
 }
 static int grid_slots(const DeviceInfo& d) { const int r = g_sm_reserve.load(); return d.sms - r > 0 ? d.sms - r : 1; }   // see b2s_set_sm_reserve
 
-template <class K> static int allow_smem(K kern, int bytes) {
+// Opt-in to > 48 KB of dynamic shared memory, once per kernel and device.  `TAG` makes the flag array unique per KERNEL
+// (kernels of different plans share a function-pointer type, so the pointer type alone is not a key); setting the
+// attribute twice is harmless.
+template <class TAG, class K> static int allow_smem(K kern, int bytes) {
   int dev = 0;
   B2S_CUDA(cudaGetDevice(&dev));
-  static std::atomic<bool> configured[64];    // per kernel instantiation and device; setting the attribute twice is harmless
+  static std::atomic<bool> configured[64];
   if (!configured[dev & 63].load()) {
     B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     configured[dev & 63].store(true);
   }
   return B2S_OK;
 }
+template <class... T> struct KernelTag {};
 
 // REVERSE: the kernel walks the images last-to-first (sens_reduce: it usually follows the kernel that wrote them, and
 // the end of a 192 MB stream is what is still in the 126 MB L2).  `first_image`: images before it are skipped (they
@@ -58,7 +62,7 @@ int launch_fused(const Pro& pro, const Epi& epi, float scale, int64_t n_images, 
   auto kern = fft2_half_kernel<P, Pro, Epi, CARRY, REVERSE>;
   DeviceInfo d;
   if (int rc = device_info(d)) return rc;
-  if (int rc = allow_smem(kern, Derived<P>::SMEM_BYTES)) return rc;
+  if (int rc = allow_smem<KernelTag<P, Pro, Epi, std::integral_constant<int, CARRY + 2 * REVERSE>>>(kern, Derived<P>::SMEM_BYTES)) return rc;
   const int n_items = (int)(P::FOLD * n_images), item0 = (int)(P::FOLD * first_image);
   const int slots = grid_slots(d) * P::CTAS;
   const unsigned grid = (unsigned)(n_items - item0 < slots ? n_items - item0 : slots);   // persistent: P::CTAS CTAs per SM
@@ -78,7 +82,7 @@ int launch_packed(const Pro& pro, const Epi& epi, const TailEpi& tail_epi, float
   constexpr int SMEM = PkSmem<PK200, Epi>::BYTES;
   DeviceInfo d;
   if (int rc = device_info(d)) return rc;
-  if (int rc = allow_smem(kern, SMEM)) return rc;
+  if (int rc = allow_smem<KernelTag<PK200, Pro, Epi, std::integral_constant<int, QD * 100 + TT * 10 + CARRY + 2 * REVERSE>>>(kern, SMEM)) return rc;
   const int slots = grid_slots(d);
   int64_t n_whole = n_images;
   const int64_t rem = n_images % slots;

@@ -528,6 +528,32 @@ def test_autograd_matches_torch_reference(ops, hw):
         assert err <= 5e-5, (name, err)
 
 
+def test_autograd_xpdnet_chain(ops):
+    """Gradients of the XPDNet K/I pair (xpdnet.py:295-298, 372-446): r = M A x - y, then A^H (M r), w.r.t. image and
+    sensitivity maps, against the torch restatement."""
+    fft2c, ifft2c, cmul, conj = _torch_ref_ops()
+    b, t, c, h, w = 1, 2, 3, 200, 200
+    cs = G.sense_case(78, b, t, c, h, w)
+    mask = cu(cs["mask"]); mf = mask.float()
+    ref = cu(cs["ref"])
+
+    def run(ours):
+        img = cu(cs["img"]).requires_grad_(True); sens = cu(cs["sens"]).requires_grad_(True)
+        if ours:
+            r = ops.sens_expand(img, sens, ops.EXPAND_RESIDUAL, ref=ref, mask=mask)
+            out = ops.sens_reduce(r, sens, mask=mask)
+        else:
+            r = fft2c(cmul(img, sens)) * mf - ref
+            out = cmul(ifft2c(r * mf), conj(sens)).sum(2)
+        wgt = torch.linspace(0.5, 1.5, out.numel(), device="cuda").view_as(out)
+        ((out * wgt).sum() + 0.1 * (r * r).sum()).backward()
+        return img.grad, sens.grad
+
+    for ga, gr, name in zip(run(True), run(False), ("img", "sens")):
+        err = float((ga - gr).abs().max() / gr.abs().max())
+        assert err <= 5e-5, (name, err)
+
+
 def test_autograd_fft_and_pointwise(ops, F):
     fft2c, ifft2c, cmul, conj = _torch_ref_ops()
     x = cu(G.rng_normal(5, (2, 200, 200, 2))).requires_grad_(True)

