@@ -31,6 +31,7 @@ SIGNATURES = {
     "b2s_fft1c": [_p, _p, _i64, _i, _i64, _i, _i, _i, _i, _p],
     "b2s_sens_expand": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p],
     "b2s_sens_reduce": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p],
+    "b2s_apply_mask": [_p, _p, _p, _i64, _i, _i, _i, _p],
     "b2s_dc_blend": [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _p],
     "b2s_dc_blend_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p],
     "b2s_complex_mul": [_p, _p, _p, _i, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), _i, _p],

@@ -63,7 +63,7 @@ __global__ void row_weight_kernel(const cfloat* k, cfloat* out, const uint8_t* m
     const long long row = i / W, y = row % H, bt = row / H / C;
     const float wgt = wa + wb * (float)mask[bt * H + y];
     const cfloat z = k[i];
-    out[i] = make_c(z.x * wgt, z.y * wgt);
+    out[i] = make_c(z.x * wgt + 0.f, z.y * wgt + 0.f);      // (+ 0.0 as the reference: no negative zeros, transforms.py:90)
   }
 }
 
@@ -442,6 +442,14 @@ int launch_coil_reduce(const float* y, const float* mult, float* out, int over_f
 }
 
 }  // namespace b2s
+
+// apply_mask (data/transforms.py:66-92): out = k * m + 0.0 with the (b,t,h) row mask broadcast over coils and columns
+extern "C" int b2s_apply_mask(const float* kspace, const uint8_t* mask, float* out, int64_t n_bt, int c, int h, int w, void* stream) {
+  if (n_bt < 0 || c < 0 || h < 0 || w < 0) return fail(B2S_EINVAL, "b2s_apply_mask: bad argument");
+  if (n_bt * c * (long long)h * w == 0) return B2S_OK;
+  if (!kspace || !mask || !out) return fail(B2S_EINVAL, "b2s_apply_mask: null pointer");
+  return launch_row_weight(kspace, out, mask, nullptr, 1, n_bt, c, h, w, (cudaStream_t)stream);
+}
 
 extern "C" int b2s_upload_rows(const float* kspace_host, const uint8_t* mask, float* kspace_dev, int64_t n_bt, int c, int h,
                                int w, void* stream) {

@@ -104,6 +104,12 @@ int b2s_sens_reduce(const float* kspace, const float* mult, float* out, const ui
                     const float* v, int weight_mode, int over_frames, int b, int t, int c, int h,
                     int w, int norm, void* scratch, size_t scratch_bytes, void* stream);
 
+/* apply_mask - data/transforms.py:66-92 (the multiplication; the mask itself comes from the host-side mask functions,
+ * data/subsample.py:75-215, restated in deep_cine_cardiac_mri_b200/masks.py): out = kspace * m + 0.0, mask (n_bt, h) uint8
+ * broadcast over coils and columns. */
+int b2s_apply_mask(const float* kspace, const uint8_t* mask, float* out, int64_t n_bt, int c, int h, int w,
+                   void* stream);
+
 /* Stand-alone soft data-consistency blend — varnet.py:281-282. n_bt = b*t. */
 int b2s_dc_blend(const float* kspace, const float* ref, const uint8_t* mask, const float* v,
                  float* out, int64_t n_bt, int c, int h, int w, void* stream);
