@@ -55,6 +55,11 @@ def load(models: bool = True):
         raise RuntimeError("the reference is not available: run __graft_entry__.build() where /root/reference exists")
     if str(root) not in sys.path:
         sys.path.insert(0, str(root))
+    loaded = sys.modules.get("reconstruction")
+    if loaded is not None and not str(getattr(loaded, "__file__", "") or "").startswith(str(root)):
+        for name in [n for n in sys.modules if n == "reconstruction" or n.startswith("reconstruction.")]:
+            del sys.modules[name]                                    # a different `reconstruction` (e.g. a test double) was imported
+        sys.path.remove(str(root)); sys.path.insert(0, str(root))
     for name in ("bart", "h5py"):
         if name not in sys.modules:
             try:
