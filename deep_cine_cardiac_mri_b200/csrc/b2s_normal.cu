@@ -1,24 +1,32 @@
-// Launcher of the on-chip CineNet normal operator (normal_core.cuh); other
+// Launcher of the on-chip CineNet normal operator (normal_warp.cuh); other
 // heights are composed from the expand / reduce operators by the Python layer.
 #include "b2s_common.cuh"
-#include "normal_core.cuh"
+#include "normal_warp.cuh"
+#include <stdlib.h>
 
 using namespace b2s;
+
+template <class P> static int launch_warp(const NormalArgs& a, long long items, cudaStream_t st) {
+  B2S_CUDA(cudaFuncSetAttribute(normal_warp_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES));
+  const unsigned blocks = (unsigned)((items + P::WARPS - 1) / P::WARPS);
+  normal_warp_kernel<P><<<blocks, P::NT, P::SMEM_BYTES, st>>>(a, items);
+  return check_launch("normal_warp_kernel");
+}
 
 static int launch_normal(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out, int mode,
                          const float* ssq, const float* bref, int b, int t, int c, int h, int w, void* stream) {
   if (!x || !sens || !mask || !v || !out || b < 0 || t < 0 || c < 0 || (mode == 1 && (!ssq || !bref)))
     return fail(B2S_EINVAL, "b2s_normal_op: bad argument");
-  typedef NormalPlan<200, 20> P;
-  if (h != P::H || w % P::XC != 0) return fail(B2S_EUNSUPPORTED, "b2s_normal_op: needs h == 200 and w % 20 == 0");
-  const long long blocks = (long long)b * t * (w / P::XC);
-  if (blocks == 0) return B2S_OK;
-  if (blocks > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "b2s_normal_op: too many frames");
   NormalArgs a; a.x = (const cfloat*)x; a.sens = (const cfloat*)sens; a.mask = mask; a.vptr = v; a.out = (cfloat*)out;
   a.T = t; a.C = c; a.W = w; a.mode = mode; a.ssq = ssq; a.bref = (const cfloat*)bref;
-  B2S_CUDA(cudaFuncSetAttribute(normal_op_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES));
-  normal_op_kernel<P><<<(unsigned)blocks, P::NT, P::SMEM_BYTES, (cudaStream_t)stream>>>(a);
-  return check_launch("normal_op_kernel");
+  if ((h != 200 && h != 256) || w % 4 != 0 || w <= 0)
+    return fail(B2S_EUNSUPPORTED, "b2s_normal_op: needs h in {200, 256} and w % 4 == 0");
+  const long long items = (long long)b * t * (w / 4);
+  if (items == 0) return B2S_OK;
+  if (items > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "b2s_normal_op: too many frames");
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (h == 200) return w == 200 ? launch_warp<NormalWarpPlan<200, 200, 11>>(a, items, st) : launch_warp<NormalWarpPlan<200, 0, 11>>(a, items, st);
+  return w == 256 ? launch_warp<NormalWarpPlan<256, 256, 8>>(a, items, st) : launch_warp<NormalWarpPlan<256, 0, 8>>(a, items, st);
 }
 
 extern "C" int b2s_normal_op(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out,

@@ -227,7 +227,8 @@ def raw_normal_dc(x, sens, mask_u8, v, ssq, bref):
 
 
 def normal_op_supported(h: int, w: int) -> bool:
-    return h == 200 and w % 20 == 0
+    """Shapes of the on-chip normal operator (csrc/normal_warp.cuh): 200 or 256 rows, 4-column groups."""
+    return h in (200, 256) and w > 0 and w % 4 == 0
 
 
 def raw_temporal_pre(image, xf: bool):

@@ -153,7 +153,8 @@ int b2s_temporal_post(const float* x, const float* mean, float* out, int b, int 
 
 /* CineNet normal operator and CG — cinenet.py:121-171, recurrent_cinenet.py:74-124.
  * H x = A^H M A x + v x with the k-space kept on chip: because the mask only selects rows,
- * F_w cancels and H x = sum_c conj(S_c) * (F_h^H M F_h)(S_c x) + v x.  x, out (b,t,h,w,2). */
+ * F_w cancels and H x = sum_c conj(S_c) * (F_h^H M F_h)(S_c x) + v x.  x, out (b,t,h,w,2).
+ * h in {200, 256}, w % 4 == 0 (B2S_EUNSUPPORTED otherwise: compose b2s_sens_expand / b2s_sens_reduce). */
 int b2s_normal_op(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out,
                   int b, int t, int c, int h, int w, void* stream);
 /* One VarNet cascade's data-consistency step entirely in the image domain (k-space never exists):

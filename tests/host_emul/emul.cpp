@@ -128,23 +128,18 @@ int emu_sens_reduce(const float* k, const float* mult, float* out, const uint8_t
 
 }  // extern "C"
 
-#include "normal_core.cuh"
-extern "C" int emu_normal_op(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out,
-                             int b, int t, int c, int h, int w) {
-  typedef NormalPlan<200, 20> P;
-  if (h != 200 || w % 20) return 2;
+#include "normal_warp.cuh"
+// warp-private on-chip normal operator (the product kernel of b2s_normal_op / b2s_normal_dc), executed lane by lane:
+// mode 0 = normal operator, mode 1 = image-domain VarNet cascade; fixed == 1 takes the compile-time-width plan
+extern "C" int emu_normal_warp(const float* x, const float* sens, const uint8_t* mask, const float* v, const float* ssq,
+                               const float* bref, float* out, int mode, int b, int t, int c, int h, int w, int fixed) {
+  if ((h != 200 && h != 256) || w % 4) return 2;
+  if (fixed && w != h) return 2;
   NormalArgs a; a.x = (const cfloat*)x; a.sens = (const cfloat*)sens; a.mask = mask; a.vptr = v; a.out = (cfloat*)out;
-  a.T = t; a.C = c; a.W = w; a.mode = 0; a.ssq = nullptr; a.bref = nullptr;
-  normal_op_emulate<P>(a, (long long)b * t);
-  return 0;
-}
-extern "C" int emu_normal_dc(const float* x, const float* sens, const uint8_t* mask, const float* v, const float* ssq,
-                             const float* bref, float* out, int b, int t, int c, int h, int w) {
-  typedef NormalPlan<200, 20> P;
-  if (h != 200 || w % 20) return 2;
-  NormalArgs a; a.x = (const cfloat*)x; a.sens = (const cfloat*)sens; a.mask = mask; a.vptr = v; a.out = (cfloat*)out;
-  a.T = t; a.C = c; a.W = w; a.mode = 1; a.ssq = ssq; a.bref = (const cfloat*)bref;
-  normal_op_emulate<P>(a, (long long)b * t);
+  a.T = t; a.C = c; a.W = w; a.mode = mode; a.ssq = ssq; a.bref = (const cfloat*)bref;
+  const long long n = (long long)b * t;
+  if (h == 200) { if (fixed) normal_warp_emulate<NormalWarpPlan<200, 200, 11>>(a, n); else normal_warp_emulate<NormalWarpPlan<200, 0, 11>>(a, n); }
+  else          { if (fixed) normal_warp_emulate<NormalWarpPlan<256, 256, 8>>(a, n); else normal_warp_emulate<NormalWarpPlan<256, 0, 8>>(a, n); }
   return 0;
 }
 

@@ -161,28 +161,23 @@ def test_emulated_sense_operators(emu, variant, hw):
     assert rel(out, want_s) <= 1e-6
 
 
-def test_emulated_normal_operator(emu):
-    b, t, c, h, w = 1, 2, 3, 200, 200
-    cs = G.sense_case(9, b, t, c, h, w)
-    d = {k: (a.astype(np.float64) if getattr(a, "dtype", None) == np.float32 and a.ndim else a) for k, a in cs.items()}
-    v = np.array([O.softplus(cs["lam"])], dtype=np.float32)
-    out = np.empty((b, t, 1, h, w, 2), np.float32)
-    assert emu.emu_normal_op(P(cs["img"]), P(cs["sens"]), P(cs["mask"]), P(v), P(out), b, t, c, h, w) == 0
-    assert rel(out, O.normal_op(d["img"], d["mask"], d["sens"], float(v[0]))) <= 1e-6
-
-
-def test_emulated_image_domain_cascade(emu):
-    """b2s_normal_dc == A^H[DC(A x, ref)] (one VarNet cascade without materialising k-space)."""
-    b, t, c, h, w = 1, 2, 3, 200, 200
-    cs = G.sense_case(9, b, t, c, h, w)
+@pytest.mark.parametrize("h,w,fixed", [(200, 200, 1), (200, 200, 0), (256, 256, 1), (200, 36, 0), (256, 12, 0)])
+def test_emulated_warp_private_normal_operator(emu, h, w, fixed):
+    """normal_warp.cuh (product kernel of b2s_normal_op / b2s_normal_dc) executed lane by lane on the CPU: both modes
+    (normal operator; b2s_normal_dc == A^H[DC(A x, ref)], one VarNet cascade without materialising k-space), both
+    heights, compile-time and run-time widths."""
+    b, t, c = 1, 2, 3
+    cs = G.sense_case(11, b, t, c, h, w)
     d = {k: (a.astype(np.float64) if getattr(a, "dtype", None) == np.float32 and a.ndim else a) for k, a in cs.items()}
     v = np.array([0.8], dtype=np.float32)
+    out = np.empty((b, t, 1, h, w, 2), np.float32)
+    assert emu.emu_normal_warp(P(cs["img"]), P(cs["sens"]), P(cs["mask"]), P(v), None, None, P(out), 0, b, t, c, h, w, fixed) == 0
+    assert rel(out, O.normal_op(d["img"], d["mask"], d["sens"], 0.8)) <= 1e-6
     ref_m = O.apply_mask(d["ref"], d["mask"])
     bref = np.ascontiguousarray(O.sens_reduce(ref_m, d["sens"]).astype(np.float32))
     ssq = np.ascontiguousarray((d["sens"] ** 2).sum(axis=(2, 5))[:, 0].astype(np.float32))
     want = O.sens_reduce(O.dc_blend(O.sens_expand(d["img"], d["sens"]), ref_m, d["mask"], 0.8), d["sens"])
-    out = np.empty((b, t, 1, h, w, 2), np.float32)
-    assert emu.emu_normal_dc(P(cs["img"]), P(cs["sens"]), P(cs["mask"]), P(v), P(ssq), P(bref), P(out), b, t, c, h, w) == 0
+    assert emu.emu_normal_warp(P(cs["img"]), P(cs["sens"]), P(cs["mask"]), P(v), P(ssq), P(bref), P(out), 1, b, t, c, h, w, fixed) == 0
     assert rel(out, want) <= 1e-6
 
 

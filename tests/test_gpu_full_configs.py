@@ -53,7 +53,7 @@ def case(tag):
         "fft2c": O.fft2c(d["k"][:, :2]),
         "ifft2c": O.ifft2c(d["k"][:, :2]),
     }
-    if h == 200:
+    if h in (200, 256):
         want["normal"] = O.normal_op(d["img"], d["mask"], d["sens"], v)
     _cache[tag] = (cs, v, want)
     return _cache[tag]

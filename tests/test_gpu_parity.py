@@ -118,7 +118,7 @@ def test_error_parity(F):
 
 # --------------------------------- block tier ------------------------------- #
 CASES = {"a": (1, 3, 4, 200, 200), "rag": (2, 2, 3, 200, 200), "one": (1, 1, 1, 200, 200),
-         "g256": (1, 2, 3, 256, 256), "odd": (2, 3, 2, 18, 14)}
+         "g256": (1, 2, 3, 256, 256), "odd": (2, 3, 2, 18, 14), "w36": (1, 2, 3, 200, 36)}
 
 
 def make_case(tag):
@@ -164,13 +164,14 @@ def test_sens_expand_reduce_dc(ops, tag, fused_path):
     assert rel(got, want) <= TOL
 
 
-@pytest.mark.parametrize("tag", ["a", "rag", "one"])
+@pytest.mark.parametrize("tag", ["a", "rag", "one", "g256", "w36"])
 def test_normal_op_and_cg(ops, tag):
     from deep_cine_cardiac_mri_b200 import blocks
     cs, d = make_case(tag)
     img, ref, sens, mask = (cu(cs[n]) for n in ("img", "ref", "sens", "mask"))
     v = float(O.softplus(cs["lam"]))
     want = O.normal_op(d["img"], d["mask"], d["sens"], v)
+    assert ops.normal_op_supported(*img.shape[3:5])       # the on-chip kernel (200 or 256 rows, any width % 4 == 0)
     assert rel(ops.normal_op(img.squeeze(2), sens, mask, v).unsqueeze(2), want) <= TOL
     # composed path (used when sens needs grad / other sizes) agrees too
     comp = ops.sens_reduce(ops.sens_expand(img, sens, ops.EXPAND_MASK, mask=mask), sens) + v * img.squeeze(2)
