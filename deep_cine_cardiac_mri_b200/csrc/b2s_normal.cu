@@ -2,7 +2,6 @@
 // heights are composed from the expand / reduce operators by the Python layer.
 #include "b2s_common.cuh"
 #include "normal_warp.cuh"
-#include <stdlib.h>
 
 using namespace b2s;
 
@@ -25,8 +24,8 @@ static int launch_normal(const float* x, const float* sens, const uint8_t* mask,
   if (items == 0) return B2S_OK;
   if (items > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "b2s_normal_op: too many frames");
   const cudaStream_t st = (cudaStream_t)stream;
-  if (h == 200) return w == 200 ? launch_warp<NormalWarpPlan<200, 200, 11>>(a, items, st) : launch_warp<NormalWarpPlan<200, 0, 11>>(a, items, st);
-  return w == 256 ? launch_warp<NormalWarpPlan<256, 256, 8>>(a, items, st) : launch_warp<NormalWarpPlan<256, 0, 8>>(a, items, st);
+  if (h == 200) return w == 200 ? launch_warp<NormalWarpPlan<200, 200, 3, 4>>(a, items, st) : launch_warp<NormalWarpPlan<200, 0, 3, 4>>(a, items, st);
+  return w == 256 ? launch_warp<NormalWarpPlan<256, 256, 4, 2>>(a, items, st) : launch_warp<NormalWarpPlan<256, 0, 4, 2>>(a, items, st);
 }
 
 extern "C" int b2s_normal_op(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out,

@@ -22,7 +22,9 @@
 //     fp32 (FADD2 / FMUL2 / FFMA2), half the issue slots of the scalar form.  G odd: the last quad's b half is a dummy.
 //   * centring signs (-1)^m and the 1/H scale are folded into the two twiddle tables; the mask row becomes a per-warp
 //     table of packed 0/1 factors in the order the length-8 step reads them.
-//   * S_{c+1} streams into the warp's landing buffer (8-byte cp.async, thread-private slots) behind coil c's arithmetic.
+//   * S_c is loaded straight into registers at the top of a coil (a cp.async landing buffer one coil ahead measured
+//     slower: its shared-memory wavefronts cost more than the latency the other resident warps cover anyway); CTAs are
+//     small (3-4 warps, 2-4 per SM) so that prologues and epilogues of different CTAs overlap.
 //
 // Plans: H in {200 (G = 25), 256 (G = 32)}; W compile-time (200, 256) or 0 = run-time width (any multiple of 4).
 // Emulated on the CPU by normal_warp_emulate (tests/host_emul).
@@ -44,17 +46,16 @@ struct NormalArgs {
 
 struct alignas(16) nquad { float ra, rb, ia, ib; };
 
-template <int H_, int W_, int WARPS_> struct NormalWarpPlan {
+template <int H_, int W_, int WARPS_, int CTAS_> struct NormalWarpPlan {
   static constexpr int H = H_, G = H_ / 8, XC = 4, WFIX = W_;
-  static constexpr int WARPS = WARPS_, NT = 32 * WARPS_;
+  static constexpr int WARPS = WARPS_, NT = 32 * WARPS_, CTAS = CTAS_;   // CTAS: resident CTAs per SM the registers are budgeted for
   static constexpr int NP = (G + 1) / 2;                      // quads (pairs of adjacent g) per (m, xl)
   static constexpr int EPQ = 8 * XC + 4;                      // quads per pair-block of E; 36 = 4 mod 8: step 2 conflict-free
   // per warp, in 8-byte units
   static constexpr int E_OFF = 0;                             // E[p][m][xl]   quads 0..31 of block p; the 4 padding quads hold
   static constexpr int MKQ = 8 * XC;                          // MK[p][k2] = {mask(2p + G k2), mask(2p+1 + G k2)} as floats, k2 = 0..7
   static constexpr int X_OFF = E_OFF + 2 * NP * EPQ;          // x_t   slots [i][lane]
-  static constexpr int L_OFF = X_OFF + H_ * XC;               // S_c+1 slots [i][lane]
-  static constexpr int WARP_ELEMS = L_OFF + H_ * XC;
+  static constexpr int WARP_ELEMS = X_OFF + H_ * XC;
   // per CTA
   static constexpr int TWPQ = 9;                              // quads per pair-block of the twiddle tables (odd pitch)
   static constexpr int TW1_OFF = WARPS_ * WARP_ELEMS;         // TW1[p][m] = (-1)^m w^(m g)        {c_a, c_b, s_a, s_b}
@@ -101,38 +102,15 @@ B2S_HD void nw_stage(const NormalArgs& a, cfloat* ws, long long bt, int x0, int 
   }
 }
 
-// asynchronous copy of one 8-byte element global -> shared (cp.async); a plain copy on the host
-B2S_HD void async_copy8(cfloat* dst_smem, const cfloat* src) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-#else
-  *dst_smem = *src;
-#endif
-}
-B2S_HD void async_wait_all() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
-}
-
-// this lane's G values of one coil's S into its own slots of the landing buffer (read back only by this lane)
-template <class P>
-B2S_HD void nw_prefetch_s(const NormalArgs& a, cfloat* ws, const cfloat* sp, int lane) {
-  const int w = nw_width<P>(a);
-#pragma unroll
-  for (int i = 0; i < P::G; ++i) async_copy8(ws + P::L_OFF + 32 * i + lane, sp + (size_t)i * 8 * w);
-}
-
 // step 1: p = S_c x, radix-G over this lane's rows, twiddle (with the input checkerboard), E[p][m][xl]
 template <class P>
-B2S_HD void nw_step1(const NormalArgs& a, cfloat* ws, const cfloat* smem, const cfloat* sp_next, bool has_next, int lane, cfloat (&sv)[P::G]) {
+B2S_HD void nw_step1(const NormalArgs& a, cfloat* ws, const cfloat* smem, const cfloat* sp, int lane, cfloat (&sv)[P::G]) {
   constexpr int G = P::G, NP = P::NP;
   const int m = lane >> 2;
   float re[2 * NP], im[2 * NP];
-  async_wait_all();                                       // S_c landed (issued one coil ago, slots private to this lane)
+  const int w = nw_width<P>(a);
 #pragma unroll
-  for (int i = 0; i < G; ++i) sv[i] = ws[P::L_OFF + 32 * i + lane];
-  if (has_next) nw_prefetch_s<P>(a, ws, sp_next, lane);   // S_{c+1} streams in behind this coil's arithmetic
+  for (int i = 0; i < G; ++i) sv[i] = sp[(size_t)i * 8 * w];   // S_c straight into registers: the other resident warps cover the latency
   {
     float pr[G], pi[G];
 #pragma unroll
@@ -244,7 +222,7 @@ B2S_HD void nw_finish(const NormalArgs& a, const cfloat* ws, long long bt, int x
 
 #if defined(__CUDACC__)
 template <class P>
-__global__ void __launch_bounds__(P::NT, 1) normal_warp_kernel(const NormalArgs a, long long n_items) {
+__global__ void __launch_bounds__(P::NT, P::CTAS) normal_warp_kernel(const NormalArgs a, long long n_items) {
   extern __shared__ __align__(16) unsigned char b2s_smem_raw[];
   cfloat* smem = reinterpret_cast<cfloat*>(b2s_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -259,8 +237,16 @@ __global__ void __launch_bounds__(P::NT, 1) normal_warp_kernel(const NormalArgs 
   const int x0 = (int)(item - bt * groups) * P::XC;
   const size_t hw = (size_t)P::H * w;
   const cfloat* sp = a.sens + (size_t)(bt / a.T) * a.C * hw + (size_t)(lane >> 2) * w + x0 + (lane & 3);
-  nw_prefetch_s<P>(a, ws, sp, lane);
   nw_stage<P>(a, ws, bt, x0, lane);
+  if (a.mode != 0 && (lane & 3) == 0) {                   // warm L2 with this item's bref / ssq segments (read in nw_finish)
+    const char* bp = reinterpret_cast<const char*>(a.bref + bt * hw + (size_t)(lane >> 2) * w + x0);
+    const char* dp = reinterpret_cast<const char*>(a.ssq + (bt / a.T) * hw + (size_t)(lane >> 2) * w + x0);
+#pragma unroll
+    for (int i = 0; i < P::G; ++i) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(bp + (size_t)i * 8 * w * 8));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(dp + (size_t)i * 8 * w * 4));
+    }
+  }
   float accr[P::G], acci[P::G];
   cfloat sv[P::G];
 #pragma unroll
@@ -268,8 +254,8 @@ __global__ void __launch_bounds__(P::NT, 1) normal_warp_kernel(const NormalArgs 
   __syncwarp();                                           // mask factors visible to the warp
 #pragma unroll 1
   for (int c = 0; c < a.C; ++c) {
+    nw_step1<P>(a, ws, smem, sp, lane, sv);
     sp += hw;
-    nw_step1<P>(a, ws, smem, sp, c + 1 < a.C, lane, sv);
     __syncwarp();
 #pragma unroll 1
     for (int r = 0; r < P::ROUNDS2; ++r) {
@@ -301,13 +287,11 @@ void normal_warp_emulate(const NormalArgs& a, long long n_bt) {
     const cfloat* sp[32];
     for (int lane = 0; lane < 32; ++lane) {
       sp[lane] = a.sens + (size_t)(bt / a.T) * a.C * hw + (size_t)(lane >> 2) * w + x0 + (lane & 3);
-      nw_prefetch_s<P>(a, ws, sp[lane], lane);
       nw_stage<P>(a, ws, bt, x0, lane);
       for (int k = 0; k < P::G; ++k) { accr[lane][k] = 0.f; acci[lane][k] = 0.f; }
     }
     for (int c = 0; c < a.C; ++c) {
-      // (the host's async_copy8 is immediate: a lane's prefetch of S_{c+1} overwrites only its own, already read, slots)
-      for (int lane = 0; lane < 32; ++lane) { sp[lane] += hw; nw_step1<P>(a, ws, smem, sp[lane], c + 1 < a.C, lane, sv[lane]); }
+      for (int lane = 0; lane < 32; ++lane) { nw_step1<P>(a, ws, smem, sp[lane], lane, sv[lane]); sp[lane] += hw; }
       for (int task = 0; task < P::TASKS2; ++task) nw_step2<P>(ws, smem, task);
       for (int lane = 0; lane < 32; ++lane) nw_step3<P>(ws, lane, sv[lane], accr[lane], acci[lane]);
     }
