@@ -43,6 +43,9 @@ SIGNATURES = {
     "b2s_rss_normalize_bwd": [_p, _p, _p, _i, _i, _i64, _p],
     "b2s_temporal_pre": [_p, _p, _p, _i, _i, _i64, _i, _p],
     "b2s_temporal_post": [_p, _p, _p, _i, _i, _i64, _i, _p],
+    "b2s_planes_stats": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "b2s_planes_pack": [_p, _p, _p, _p, _p] + [_i] * 10 + [_p],
+    "b2s_planes_unpack": [_p, _p, _p, _p, _p] + [_i] * 10 + [_p],
     "b2s_normal_op": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2s_normal_dc": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2s_dot": [_p, _p, _p, _i64, _p, _p],

@@ -29,6 +29,27 @@ def sens_reduce(self, x: torch.Tensor, sens_maps: torch.Tensor) -> torch.Tensor:
     return ops.sens_reduce(x, sens_maps).unsqueeze(2)
 
 
+_PLANE_GLUE = True
+
+
+def set_plane_glue_inference(on: bool) -> None:
+    """Fused x-f / y-f plane packing around the regularisers under torch.no_grad() (default on); off = the reference's
+    permute / view / NormUnet glue in eager torch (always used when autograd is recording)."""
+    global _PLANE_GLUE
+    _PLANE_GLUE = bool(on)
+
+
+def _plane_glue_ok(x: torch.Tensor) -> bool:
+    return _PLANE_GLUE and x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad) \
+        and not torch.is_grad_enabled()
+
+
+def _is_norm_unet(m) -> bool:
+    """A reference NormUnet (denoisers/norm_unet.py:18-114): 2-channel complex planes around `.unet`."""
+    return type(m).__name__ == "NormUnet" and hasattr(m, "unet") and getattr(m.unet, "in_chans", 2) == 2 \
+        and getattr(m.unet, "out_chans", 2) == 2
+
+
 def _xfyf(self, image_combined: torch.Tensor, run_models) -> torch.Tensor:
     """Temporal head/tail of xfyf_transform (varnet.py:196-241, cinenet.py:174-219) around the
     untouched regularisers.  image_combined (b,t,h,w,2) -> (b,t,1,h,w,2)."""
@@ -43,6 +64,14 @@ def varnet_xfyf_transform(self, image_combined: torch.Tensor) -> torch.Tensor:
     b, t, h, w, ch = image_combined.shape
 
     def run(x):
+        model_xf, model_yf = (self.model, self.model) if self.weight_sharing else self.model
+        if _plane_glue_ok(x) and _is_norm_unet(model_xf) and _is_norm_unet(model_yf):
+            # inference: the NCHW inputs of the two U-Nets (permute/view + NormUnet.complex_to_chan_dim / norm / pad,
+            # norm_unet.py:101-105) come out of one kernel pass, the U-Nets themselves run untouched, and unpad /
+            # unnorm / chan_complex_to_last_dim / the 0.5 (xf + yf) average (norm_unet.py:109-113, varnet.py:228-232)
+            # are one more launch
+            xf, yf, ctx = ops.raw_planes_pack(x, normalise=True, pad=True)
+            return ops.raw_planes_unpack(model_xf.unet(xf), model_yf.unet(yf), ctx).unsqueeze(2)
         xf = x.permute(0, 2, 3, 1, 4).reshape(b * h, 1, w, t, 2)
         yf = x.permute(0, 3, 2, 1, 4).reshape(b * w, 1, h, t, 2)
         if self.weight_sharing:
@@ -62,6 +91,12 @@ def cinenet_xfyf_transform(self, image_combined: torch.Tensor) -> torch.Tensor:
     b, t, h, w, ch = image_combined.shape
 
     def run(x):
+        if _plane_glue_ok(x):
+            # inference: the two permute/reshape copies in and the permute / average out (cinenet.py:193-212) as one
+            # launch each way; the plain U-Nets take the planes as they are (no normalisation, no padding)
+            model_xf, model_yf = (self.model, self.model) if self.weight_sharing else self.model
+            xf, yf, ctx = ops.raw_planes_pack(x, normalise=False, pad=False)
+            return ops.raw_planes_unpack(model_xf(xf), model_yf(yf), ctx).unsqueeze(2)
         xf = x.permute(0, 2, 4, 3, 1).reshape(b * h, 2, w, t)
         yf = x.permute(0, 3, 4, 2, 1).reshape(b * w, 2, h, t)
         if self.weight_sharing:

@@ -231,6 +231,45 @@ def normal_op_supported(h: int, w: int) -> bool:
     return h in (200, 256) and w > 0 and w % 4 == 0
 
 
+def _pad16(n: int):
+    """NormUnet.pad (norm_unet.py:75-86): size rounded up to a multiple of 16, (leading, trailing) zero padding."""
+    mult = ((n - 1) | 15) + 1
+    return mult, (mult - n) // 2
+
+
+def raw_planes_pack(x, normalise: bool = True, pad: bool = True):
+    """x (b,t,h,w,2) -> (xf (b*h,2,wp,tp), yf (b*w,2,hp,tp), ctx): the NCHW inputs of the x-f / y-f U-Nets
+    (varnet.py:215-216 + NormUnet.complex_to_chan_dim / norm / pad, norm_unet.py:48-86) in three launches.
+    `ctx` carries the statistics and pad sizes for raw_planes_unpack."""
+    _need_cuda(x)
+    x = _f32c(x)
+    b, t, h, w, _ = x.shape
+    (hp, ph0), (wp, pw0), (tp, pt0) = (_pad16(h), _pad16(w), _pad16(t)) if pad else ((h, 0), (w, 0), (t, 0))
+    sxf = syf = None
+    if normalise:
+        sxf = torch.empty(b * h, 2, 2, dtype=torch.float32, device=x.device)
+        syf = torch.empty(b * w, 2, 2, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().b2s_planes_stats(_p(x), _p(sxf), _p(syf), b, t, h, w, _stream()), "planes_stats")
+    xf = torch.empty(b * h, 2, wp, tp, dtype=torch.float32, device=x.device)
+    yf = torch.empty(b * w, 2, hp, tp, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().b2s_planes_pack(_p(x), _p(sxf), _p(syf), _p(xf), _p(yf), b, t, h, w, hp, wp, tp, ph0, pw0, pt0, _stream()),
+               "planes_pack")
+    return xf, yf, (sxf, syf, (b, t, h, w, hp, wp, tp, ph0, pw0, pt0))
+
+
+def raw_planes_unpack(uxf, uyf, ctx):
+    """U-Net outputs (layouts of raw_planes_pack) -> 0.5 * (xf_r + yf_r) as (b,t,h,w,2): NormUnet.unpad / unnorm /
+    chan_complex_to_last_dim (norm_unet.py:88-113) and varnet.py:228-232 in one launch."""
+    sxf, syf, dims = ctx
+    b, t, h, w, hp, wp, tp = dims[:7]
+    if tuple(uxf.shape) != (b * h, 2, wp, tp) or tuple(uyf.shape) != (b * w, 2, hp, tp):
+        raise ValueError(f"raw_planes_unpack: unexpected plane shapes {tuple(uxf.shape)}, {tuple(uyf.shape)}")
+    uxf, uyf = _f32c(uxf), _f32c(uyf)
+    out = torch.empty(b, t, h, w, 2, dtype=torch.float32, device=uxf.device)
+    _lib.check(_lib.lib().b2s_planes_unpack(_p(uxf), _p(uyf), _p(sxf), _p(syf), _p(out), *dims, _stream()), "planes_unpack")
+    return out
+
+
 def raw_temporal_pre(image, xf: bool):
     """image (b,t,h,w,2) -> (x, mean (b,h,w,2))"""
     _need_cuda(image)

@@ -151,6 +151,20 @@ int b2s_temporal_pre(const float* image, float* x, float* mean, int b, int t, in
 int b2s_temporal_post(const float* x, const float* mean, float* out, int b, int t, int64_t hw, int xf,
                       void* stream);
 
+/* Regulariser-side layout glue of the x-f / y-f planes — varnet.py:215-232 (xfyf_transform's permute/view pairs and
+ * the 0.5 (xf + yf) average) and denoisers/norm_unet.py:48-114 (NormUnet.complex_to_chan_dim / norm / pad and
+ * unpad / unnorm / chan_complex_to_last_dim around the untouched U-Net); cinenet.py:193-212 without statistics.
+ * x (b,t,h,w,2).  stats_xf (b*h,2,2) / stats_yf (b*w,2,2) = {mean, unbiased std} of the real and imaginary parts of
+ * every x-f plane (b,y) over (t,x) and every y-f plane (b,x) over (t,y) — NormUnet.norm's groups. */
+int b2s_planes_stats(const float* x, float* stats_xf, float* stats_yf, int b, int t, int h, int w, void* stream);
+/* xf (b*h,2,wp,tp), yf (b*w,2,hp,tp): the U-Nets' NCHW inputs, (x - mean)/std where statistics are given (both or
+ * neither), zero-padded: plane row r holds image column/row r - pw0 / r - ph0, plane column q holds frame q - pt0. */
+int b2s_planes_pack(const float* x, const float* stats_xf, const float* stats_yf, float* xf, float* yf,
+                    int b, int t, int h, int w, int hp, int wp, int tp, int ph0, int pw0, int pt0, void* stream);
+/* out (b,t,h,w,2) = 0.5 * (unnorm(unpad(uxf)) + unnorm(unpad(uyf))) from the U-Net outputs (same layouts as above). */
+int b2s_planes_unpack(const float* uxf, const float* uyf, const float* stats_xf, const float* stats_yf, float* out,
+                      int b, int t, int h, int w, int hp, int wp, int tp, int ph0, int pw0, int pt0, void* stream);
+
 /* CineNet normal operator and CG — cinenet.py:121-171, recurrent_cinenet.py:74-124.
  * H x = A^H M A x + v x with the k-space kept on chip: because the mask only selects rows,
  * F_w cancels and H x = sum_c conj(S_c) * (F_h^H M F_h)(S_c x) + v x.  x, out (b,t,h,w,2).

@@ -226,3 +226,83 @@ def test_xpdnet_block_bodies_match_reference(rec):
     # against the fp64 oracle at 1e-5): their difference may reach 2e-5
     assert relmax(outs[True][0], outs[False][0]) <= 2e-5
     assert relmax(outs[True][1], outs[False][1]) <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------ #
+# regulariser-side layout glue: plane packing around the REAL NormUnet / Unet
+# ------------------------------------------------------------------------------------------------------------------ #
+@pytest.mark.parametrize("shape", [(2, 15, 200, 200), (1, 7, 24, 40), (1, 30, 256, 256), (1, 16, 32, 48)])
+def test_plane_pack_unpack_against_reference_normunet_glue(rec, shape):
+    """b2s_planes_stats / pack / unpack against the reference's own glue: the permute/view pairs of
+    VarNetBlock.xfyf_transform (varnet.py:215-216, 228-232) and NormUnet.complex_to_chan_dim / norm / pad / unpad /
+    unnorm / chan_complex_to_last_dim (norm_unet.py:48-113), run in fp64 torch as the arbiter."""
+    from deep_cine_cardiac_mri_b200 import ops
+    from reconstruction.models.denoisers.norm_unet import NormUnet
+    b, t, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(b, t, h, w, 2, device="cuda", generator=g) * 3 + 0.7
+    nu = NormUnet(4, 2).cuda().double()
+    x64 = x.double()
+    xf_ref = x64.clone().permute(0, 2, 3, 1, 4).reshape(b * h, 1, w, t, 2)
+    yf_ref = x64.clone().permute(0, 3, 2, 1, 4).reshape(b * w, 1, h, t, 2)
+    want, keep = [], []
+    for z in (xf_ref, yf_ref):
+        zz, mean, std = nu.norm(nu.complex_to_chan_dim(z))
+        zz, pads = nu.pad(zz)
+        want.append(zz); keep.append((mean, std, pads))
+    xf, yf, ctx = ops.raw_planes_pack(x, normalise=True, pad=True)
+    assert xf.shape == want[0].shape and yf.shape == want[1].shape
+    assert relmax(xf, want[0]) <= 2e-6 and relmax(yf, want[1]) <= 2e-6
+    # the way back: feed "U-Net outputs" u (a fixed pointwise function of the inputs) through both paths
+    f = lambda z: torch.tanh(z) * 1.5 + 0.25 * z                                       # noqa: E731
+    back = []
+    for z, (mean, std, pads) in zip(want, keep):
+        back.append(nu.chan_complex_to_last_dim(nu.unnorm(nu.unpad(f(z), *pads), mean, std)))
+    xf_r = back[0].view(b, h, 1, w, t, 2).permute(0, 4, 2, 1, 3, 5)
+    yf_r = back[1].view(b, w, 1, h, t, 2).permute(0, 4, 2, 3, 1, 5)
+    want_out = (0.5 * (xf_r + yf_r)).squeeze(2)
+    got = ops.raw_planes_unpack(f(xf), f(yf), ctx)
+    assert relmax(got, want_out) <= 5e-6
+    # bare permutation (CineNet's plain Unet, cinenet.py:193-212): exact
+    xf2, yf2, ctx2 = ops.raw_planes_pack(x, normalise=False, pad=False)
+    assert torch.equal(xf2, x.permute(0, 2, 4, 3, 1).reshape(b * h, 2, w, t))
+    assert torch.equal(yf2, x.permute(0, 3, 4, 2, 1).reshape(b * w, 2, h, t))
+    xr = xf2.view(b, h, 1, 2, w, t).permute(0, 5, 2, 1, 4, 3)
+    yr = yf2.view(b, w, 1, 2, h, t).permute(0, 5, 2, 4, 1, 3)
+    assert torch.equal(ops.raw_planes_unpack(xf2, yf2, ctx2), (0.5 * (xr + yr)).squeeze(2))
+
+
+@pytest.mark.parametrize("kind", ["varnet_xf", "varnet_xt_shared", "cinenet_xf"])
+def test_xfyf_transform_fast_glue_on_real_blocks(rec, kind):
+    """xfyf_transform of the real VarNetBlock (NormUnet pair) / CineNetBlock (Unet pair) under no_grad: patched with the
+    fused plane glue == patched with the reference's eager glue == the unpatched reference, through the real U-Nets."""
+    from reconstruction.models import varnet, cinenet
+    from reconstruction.models.denoisers.norm_unet import NormUnet
+    from reconstruction.models.denoisers.unet import Unet
+    from deep_cine_cardiac_mri_b200 import _lib
+    torch.manual_seed(3)
+    if kind == "varnet_xf":
+        blk = varnet.VarNetBlock(torch.nn.ModuleList([NormUnet(6, 2), NormUnet(6, 2)]), "XF", False).cuda().eval()
+    elif kind == "varnet_xt_shared":
+        blk = varnet.VarNetBlock(NormUnet(6, 2), "XT", True).cuda().eval()
+    else:
+        blk = cinenet.CineNetBlock(torch.nn.ModuleList([Unet(6, 2, dims=2), Unet(6, 2, dims=2)]), 4, "XF", False).cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    img = torch.randn(1, 15, 200, 200, 2, device="cuda", generator=g)
+    with torch.no_grad():
+        patch.unpatch_reference()
+        ref = blk.xfyf_transform(img)
+        patch.patch_reference()
+        try:
+            blocks.set_plane_glue_inference(False)
+            eager = blk.xfyf_transform(img)
+            blocks.set_plane_glue_inference(True)
+            n0 = _lib.lib().b2s_launch_count(0)
+            fast = blk.xfyf_transform(img)
+            launched = _lib.lib().b2s_launch_count(0) - n0
+        finally:
+            blocks.set_plane_glue_inference(True)
+            patch.unpatch_reference()
+    assert relmax(eager, ref) <= 1e-5
+    assert relmax(fast, ref) <= 1e-5
+    assert launched >= 4            # temporal head + (stats) + pack + unpack + temporal tail really ran on our kernels
