@@ -267,6 +267,7 @@ def run_ours(args, rank, world, local):
         bdist.barrier()
     lib = _lib.lib()
     nb, K, W = CFG["slices_per_gpu_step"], args.steps, args.warmup
+    numa = bdist.bind_host_memory_to_gpu(local)   # pinned buffers on the GPU's own memory node (matters at 8 ranks)
     mk_np, mask_np = make_inputs(rank, nb)
     mk_host = torch.from_numpy(mk_np).pin_memory()
     mask_host = torch.from_numpy(mask_np).pin_memory()
@@ -462,7 +463,8 @@ def run_ours(args, rank, world, local):
         "e2e": {"value": world * nb * K / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "h2d": f"sampled k-space rows only ({h2d_bytes / 1e6:.0f} of {mk_host.numel() * 4 / 1e6:.0f} MB dense), read from pinned memory by "
                        f"{CFG['upload_sms']} SMs reserved for the upload",
-                "d2h_bytes_per_step": int(b * t * h * w * 4)},
+                "d2h_bytes_per_step": int(b * t * h * w * 4),
+                "host_numa": numa},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(), "traffic_source": "ncu dram__bytes of the committed capture (profiles/), not measured in this run",

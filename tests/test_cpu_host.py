@@ -407,3 +407,10 @@ def test_dispatcher_custom_ops_registered_with_fake_kernels():
         assert tuple(T.normal_op(x, s, m, v).shape) == tuple(x.shape)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         T.fft2c(torch.zeros(1, 4, 4, 2), False, 1)
+
+
+def test_numa_binding_helper_is_best_effort():
+    """dist.bind_host_memory_to_gpu never raises (no GPU / no sysfs NUMA entries here) and reports what it did."""
+    from deep_cine_cardiac_mri_b200 import dist
+    info = dist.bind_host_memory_to_gpu(0)
+    assert set(info) == {"node", "cpus", "mempolicy"}
