@@ -111,11 +111,16 @@ def strip_status() -> int:
     return int(_lib.lib().b2s_debug_strip_status())
 
 
-def upload_masked_kspace(kspace_host: torch.Tensor, mask_dev: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+def upload_masked_kspace(kspace_host: torch.Tensor, mask_dev: torch.Tensor, out: torch.Tensor = None, verify: bool = False) -> torch.Tensor:
     """Sparse host->device upload of a masked k-space (what data/transforms.py:66-92 apply_mask leaves: unsampled
     rows are zero).  `kspace_host` (b,t,c,h,w,2) float32 in PINNED host memory, `mask_dev` the (b,t,1,h,1,1) / (b,t,h)
     uint8 mask already on the device.  Only the sampled rows cross PCIe (the GPU reads them in place over UVA), the
-    others are written as zeros; runs on the current stream."""
+    others are written as zeros; runs on the current stream.
+
+    PRECONDITION: the unsampled rows of `kspace_host` are zero (true for `apply_mask` output, which is what the
+    reference's models are fed, mri_module / transforms.py:66-92).  A k-space that is NOT masked gives a different
+    result from a dense copy without any error; `verify=True` checks the precondition on the host first (reads the whole
+    buffer and synchronises - for tests and debugging) and raises ValueError when it does not hold."""
     if kspace_host.is_cuda or not kspace_host.is_pinned():
         raise ValueError("upload_masked_kspace: kspace_host must be a pinned host tensor")
     if kspace_host.dtype != torch.float32 or kspace_host.dim() != 6 or kspace_host.shape[-1] != 2 or not kspace_host.is_contiguous():
@@ -123,6 +128,11 @@ def upload_masked_kspace(kspace_host: torch.Tensor, mask_dev: torch.Tensor, out:
     _need_cuda(mask_dev)
     b, t, c, h, w, _ = kspace_host.shape
     m = _mask_u8(mask_dev, b, t, h)
+    if verify:
+        off = (m == 0).cpu().view(b, t, 1, h, 1, 1)
+        if bool((kspace_host * off).ne(0).any()):
+            raise ValueError("upload_masked_kspace: kspace_host has non-zero samples on rows the mask does not select "
+                             "(the sparse upload needs apply_mask output; use a dense .to(device) copy otherwise)")
     if out is None:
         out = torch.empty(kspace_host.shape, dtype=torch.float32, device=mask_dev.device)
     _lib.check(_lib.lib().b2s_upload_rows(C.c_void_p(kspace_host.data_ptr()), _p(m), _p(out), b * t, c, h, w, _stream()), "upload_rows")

@@ -603,6 +603,14 @@ def test_sparse_upload_of_masked_kspace(ops):
         ops.set_sm_reserve(0)
     with pytest.raises(ValueError):
         ops.upload_masked_kspace(torch.zeros(1, 1, 1, 4, 4, 2), cu(np.ones((1, 1, 1, 4, 1, 1), np.uint8)))
+    # the precondition (unsampled rows are zero) is checkable: apply_mask output passes, an unmasked k-space is refused
+    case = synth.cine_case(78, 1, 2, 2, 18, 7)
+    mask = cu(case["mask"])
+    ok = torch.from_numpy(case["masked_kspace"]).pin_memory()
+    assert torch.equal(ops.upload_masked_kspace(ok, mask, verify=True).cpu(), ok)
+    dense = torch.from_numpy(case["masked_kspace"] + 1.0).pin_memory()
+    with pytest.raises(ValueError, match="rows the mask does not select"):
+        ops.upload_masked_kspace(dense, mask, verify=True)
 
 
 def test_dc_step_host_entry():
