@@ -44,7 +44,8 @@ SIGNATURES = {
     "b2s_temporal_pre": [_p, _p, _p, _i, _i, _i64, _i, _p],
     "b2s_temporal_post": [_p, _p, _p, _i, _i, _i64, _i, _p],
     "b2s_planes_stats": [_p, _p, _p, _i, _i, _i, _i, _p],
-    "b2s_planes_pack": [_p, _p, _p, _p, _p] + [_i] * 10 + [_p],
+    "b2s_planes_scratch_bytes": [_i, _i, _i, _i],
+    "b2s_planes_pack": [_p, _p, _p, _p, _p] + [_i] * 10 + [_p, _sz, _p],
     "b2s_planes_unpack": [_p, _p, _p, _p, _p] + [_i] * 10 + [_p],
     "b2s_normal_op": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2s_normal_dc": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
@@ -62,7 +63,7 @@ SIGNATURES = {
     "b2s_err_stats": [_p, _p, _i64, _p, _p, _p],
 }
 _RESTYPE = {"b2s_launch_count": C.c_ulonglong, "b2s_last_error": C.c_char_p, "b2s_scratch_bytes": _sz, "b2s_dc_step_ws_bytes": _sz,
-            "b2s_ssim_scratch_floats": _sz}
+            "b2s_ssim_scratch_floats": _sz, "b2s_planes_scratch_bytes": _sz}
 
 
 def build(verbose: bool = False) -> Path:

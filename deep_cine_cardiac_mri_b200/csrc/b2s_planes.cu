@@ -10,8 +10,11 @@
 //                      imaginary parts of every x-f plane (b, y) over (t, x) and of every y-f plane (b, x) over (t, y),
 //                      accumulated in double, reduced in a fixed order (bit-reproducible)
 //   b2s_planes_pack    x -> xf (b*h, 2, wp, tp) and yf (b*w, 2, hp, tp): the U-Nets' NCHW inputs, normalised
-//                      ((x - mean) / std, NormUnet.norm) and zero-padded to multiples of 16 (NormUnet.pad) in one pass;
-//                      without statistics (CineNet's plain Unet, cinenet.py:193-196) it is the bare permutation
+//                      ((x - mean) / std, NormUnet.norm) and zero-padded to multiples of 16 (NormUnet.pad).  The x-f
+//                      kernel holds a whole (b, y) plane in shared memory, so it computes that plane's statistics,
+//                      writes the plane, and leaves per-row partial sums of every column for the y-f statistics - x
+//                      is read twice in total.  Without statistics (CineNet's plain Unet, cinenet.py:193-196) it is
+//                      the bare permutation
 //   b2s_planes_unpack  U-Net outputs -> 0.5 * (unnorm(unpad(xf)) + unnorm(unpad(yf))) as (b,t,h,w,2)
 //
 // All transposes go through shared-memory tiles so that both the global reads and the global writes are contiguous
@@ -23,6 +26,7 @@ using namespace b2s;
 namespace {
 
 constexpr int NT = 256;
+constexpr int U = 8;        // independent global loads in flight per thread in the tile fills
 
 struct PlaneDims {
   int B, T, H, W;          // x (B,T,H,W,2)
@@ -86,26 +90,81 @@ __global__ void __launch_bounds__(NT) stats_cols_kernel(const float* __restrict_
 // ----------------------------------------------------------------------------------------------------------------- //
 // pack
 // ----------------------------------------------------------------------------------------------------------------- //
-// x-f stack: one CTA per (b, y).  tile[t][2 W (+1)] <- T contiguous 8W-byte rows; out plane (2, WP, TP) contiguous
-__global__ void __launch_bounds__(NT) pack_xf_kernel(const float* __restrict__ x, const float* __restrict__ stats, float* __restrict__ out, PlaneDims d) {
+// x-f stack: one CTA per (b, y).  tile[t][2 W (+1)] <- T contiguous 8W-byte rows; out plane (2, WP, TP) contiguous.
+// With NORM: the plane's own statistics (thread parity = channel) and, for the y-f statistics, this row's partial sums
+// over t of every (column, channel): part[(b, y)][2 W] = {sum, sum of squares} (double).
+template <bool NORM>
+__global__ void __launch_bounds__(NT) pack_xf_kernel(const float* __restrict__ x, float* __restrict__ stats, double2* __restrict__ part,
+                                                     float* __restrict__ out, PlaneDims d) {
   extern __shared__ float tile[];
+  __shared__ double red[2][NT];
+  __shared__ float ms[4];
   const int by = blockIdx.x, b = by / d.H, y = by - b * d.H;
   const int row = 2 * d.W, pitch = row + 1;
-  for (int t = 0; t < d.T; ++t) {
-    const float* p = x + (((size_t)b * d.T + t) * d.H + y) * row;
-    for (int i = threadIdx.x; i < row; i += NT) tile[t * pitch + i] = p[i];
+  double s = 0.0, ss = 0.0;
+  {
+    // all T rows of this plane as one index space, U loads in flight per thread (row is even and NT is even: the
+    // parity of a thread's elements - its channel - is fixed)
+    const int n = d.T * row;
+    const float* p0 = x + ((size_t)b * d.T * d.H + y) * row;
+    const size_t tstride = (size_t)d.H * row;
+    for (int base = threadIdx.x; base < n; base += NT * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = base + u * NT, t = idx / row, i = idx - t * row;
+        v[u] = idx < n ? p0[t * tstride + i] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = base + u * NT, t = idx / row, i = idx - t * row;
+        if (idx < n) { tile[t * pitch + i] = v[u]; if (NORM) { s += (double)v[u]; ss += (double)v[u] * (double)v[u]; } }
+      }
+    }
   }
-  float mean[2] = {0.f, 0.f}, std[2] = {1.f, 1.f};
-  if (stats) { for (int ch = 0; ch < 2; ++ch) { mean[ch] = stats[((size_t)by * 2 + ch) * 2]; std[ch] = stats[((size_t)by * 2 + ch) * 2 + 1]; } }
+  if (NORM) { red[0][threadIdx.x] = s; red[1][threadIdx.x] = ss; }
   __syncthreads();
+  if (NORM) {
+    if (threadIdx.x < 2) {
+      double a = 0.0, c = 0.0;
+      for (int i = threadIdx.x; i < NT; i += 2) { a += red[0][i]; c += red[1][i]; }
+      float* st = stats + ((size_t)by * 2 + threadIdx.x) * 2;
+      finish_stats(a, c, (double)d.T * d.W, st);
+      ms[threadIdx.x * 2] = st[0]; ms[threadIdx.x * 2 + 1] = st[1];
+    }
+    for (int i = threadIdx.x; i < row; i += NT) {
+      double a = 0.0, c = 0.0;
+      for (int t = 0; t < d.T; ++t) { const double v = tile[t * pitch + i]; a += v; c += v * v; }
+      part[(size_t)by * row + i] = make_double2(a, c);
+    }
+    __syncthreads();
+  }
   const int plane = d.WP * d.TP;
   float* o = out + (size_t)by * 2 * plane;
   for (int i = threadIdx.x; i < 2 * plane; i += NT) {
     const int ch = i / plane, r = i - ch * plane, xp = r / d.TP, tp = r - xp * d.TP;
     const int xx = xp - d.pw0, t = tp - d.pt0;
     float v = 0.f;
-    if (xx >= 0 && xx < d.W && t >= 0 && t < d.T) { v = tile[t * pitch + 2 * xx + ch]; if (stats) v = (v - mean[ch]) / std[ch]; }
+    if (xx >= 0 && xx < d.W && t >= 0 && t < d.T) { v = tile[t * pitch + 2 * xx + ch]; if (NORM) v = (v - ms[ch * 2]) / ms[ch * 2 + 1]; }
     o[i] = v;
+  }
+}
+
+// y-f statistics from the per-row partial sums: one CTA per (b, 16 (column, channel) entries), 16 y slices per entry,
+// fixed summation order
+__global__ void __launch_bounds__(NT) col_stats_kernel(const double2* __restrict__ part, float* __restrict__ stats, PlaneDims d) {
+  __shared__ double red[2][NT];
+  const int row = 2 * d.W, groups = (row + 15) / 16;
+  const int b = blockIdx.x / groups, e = (blockIdx.x - b * groups) * 16 + (threadIdx.x & 15), ys = threadIdx.x >> 4;
+  double a = 0.0, c = 0.0;
+  if (e < row)
+    for (int y = ys; y < d.H; y += 16) { const double2 v = part[((size_t)b * d.H + y) * row + e]; a += v.x; c += v.y; }
+  red[0][threadIdx.x] = a; red[1][threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x < 16 && e < row) {
+    a = 0.0; c = 0.0;
+    for (int k = 0; k < 16; ++k) { a += red[0][k * 16 + threadIdx.x]; c += red[1][k * 16 + threadIdx.x]; }
+    finish_stats(a, c, (double)d.T * d.H, stats + ((size_t)b * row + e) * 2);      // [(b, x)][ch][2] == [b][e][2]
   }
 }
 
@@ -120,11 +179,18 @@ __global__ void __launch_bounds__(NT) pack_yf_kernel(const float* __restrict__ x
   const int yp0 = ck * YC, nyp = min(YC, d.HP - yp0);
   const int e = threadIdx.x & 15, seg = threadIdx.x >> 4;
   const int col = x0 + (e >> 1);
-  for (int s = seg; s < d.T * nyp; s += NT / 16) {
-    const int t = s / nyp, yl = s - t * nyp, y = yp0 + yl - d.ph0;
-    float v = 0.f;
-    if (y >= 0 && y < d.H && col < d.W) v = x[((((size_t)b * d.T + t) * d.H + y) * d.W + col) * 2 + (e & 1)];
-    tile[(t * nyp + yl) * 17 + e] = v;
+  for (int base = seg; base < d.T * nyp; base += (NT / 16) * U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = base + u * (NT / 16), t = s / nyp, yl = s - t * nyp, y = yp0 + yl - d.ph0;
+      v[u] = (s < d.T * nyp && y >= 0 && y < d.H && col < d.W) ? x[((((size_t)b * d.T + t) * d.H + y) * d.W + col) * 2 + (e & 1)] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = base + u * (NT / 16);
+      if (s < d.T * nyp) tile[s * 17 + e] = v[u];
+    }
   }
   __syncthreads();
   const int plane = d.HP * d.TP, blk = nyp * d.TP;
@@ -156,10 +222,24 @@ __global__ void __launch_bounds__(NT) unpack_kernel(const float* __restrict__ ux
   float* St = Bf + 2 * d.W * tpp;                 // y-f statistics of this b: [x][ch][2]
   const int planex = d.WP * d.TP, planey = d.HP * d.TP;
   const float* px = uxf + (size_t)by * 2 * planex;
-  for (int i = threadIdx.x; i < 2 * planex; i += NT) A[(i / d.TP) * tpp + i % d.TP] = px[i];
-  for (int i = threadIdx.x; i < 2 * d.W * d.TP; i += NT) {
-    const int tp = i % d.TP, xc = i / d.TP;       // xc = x * 2 + ch
-    Bf[xc * tpp + tp] = uyf[((size_t)(b * d.W) * 2 + xc) * planey + (size_t)(y + d.ph0) * d.TP + tp];
+  {
+    const int na = 2 * planex, nb = 2 * d.W * d.TP;
+    const float* py = uyf + (size_t)(b * d.W) * 2 * planey + (size_t)(y + d.ph0) * d.TP;
+    for (int base = threadIdx.x; base < na + nb; base += NT * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * NT;
+        if (i < na) v[u] = px[i];
+        else if (i < na + nb) { const int k = i - na, xc = k / d.TP, tp = k - xc * d.TP; v[u] = py[(size_t)xc * planey + tp]; }   // xc = x * 2 + ch
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * NT;
+        if (i < na) A[(i / d.TP) * tpp + i % d.TP] = v[u];
+        else if (i < na + nb) { const int k = i - na, xc = k / d.TP, tp = k - xc * d.TP; Bf[xc * tpp + tp] = v[u]; }
+      }
+    }
   }
   if (syf) for (int i = threadIdx.x; i < 4 * d.W; i += NT) St[i] = syf[(size_t)b * d.W * 4 + i];
   float mx[2] = {0.f, 0.f}, sx[2] = {1.f, 1.f};
@@ -197,24 +277,42 @@ extern "C" int b2s_planes_stats(const float* x, float* stats_xf, float* stats_yf
   return check_launch("planes_stats", 2);
 }
 
-extern "C" int b2s_planes_pack(const float* x, const float* stats_xf, const float* stats_yf, float* xf, float* yf, int b, int t, int h, int w,
-                               int hp, int wp, int tp, int ph0, int pw0, int pt0, void* stream) {
+extern "C" size_t b2s_planes_scratch_bytes(int b, int t, int h, int w) {
+  (void)t;
+  return (size_t)(b > 0 ? b : 0) * (size_t)h * (size_t)w * 2 * sizeof(double2);
+}
+
+extern "C" int b2s_planes_pack(const float* x, float* stats_xf, float* stats_yf, float* xf, float* yf, int b, int t, int h, int w,
+                               int hp, int wp, int tp, int ph0, int pw0, int pt0, void* scratch, size_t scratch_bytes, void* stream) {
   if (!x || !xf || !yf || ((stats_xf == nullptr) != (stats_yf == nullptr))) return fail(B2S_EINVAL, "b2s_planes_pack: bad pointer");
   if (int rc = check_dims("b2s_planes_pack: bad shape", b, t, h, w, hp, wp, tp, ph0, pw0, pt0)) return rc;
+  const bool norm = stats_xf != nullptr;
+  if (norm && ((long long)t * w < 2 || (long long)t * h < 2)) return fail(B2S_EINVAL, "b2s_planes_pack: planes of fewer than 2 samples have no std");
+  if (norm && (!scratch || scratch_bytes < b2s_planes_scratch_bytes(b, t, h, w) || ((uintptr_t)scratch & 15)))
+    return fail(B2S_EINVAL, "b2s_planes_pack: scratch too small or not 16-byte aligned (b2s_planes_scratch_bytes)");
   if (b == 0) return B2S_OK;
   PlaneDims d{b, t, h, w, hp, wp, tp, ph0, pw0, pt0};
+  const cudaStream_t st = (cudaStream_t)stream;
   const size_t smx = (size_t)t * (2 * w + 1) * 4;
   int yc = (int)(48 * 1024 / ((size_t)t * 17 * 4));
   if (yc < 1) yc = 1;
   if (yc > hp) yc = hp;
   const size_t smy = (size_t)t * yc * 17 * 4;
   if (smx > 200 * 1024) return fail(B2S_EUNSUPPORTED, "b2s_planes_pack: t * w too large for one shared-memory tile");
-  B2S_CUDA(cudaFuncSetAttribute(pack_xf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smx));
+  B2S_CUDA(cudaFuncSetAttribute(pack_xf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smx));
+  B2S_CUDA(cudaFuncSetAttribute(pack_xf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smx));
   B2S_CUDA(cudaFuncSetAttribute(pack_yf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smy));
-  pack_xf_kernel<<<(unsigned)(b * h), NT, smx, (cudaStream_t)stream>>>(x, stats_xf, xf, d);
+  int launches = 2;
+  if (norm) {
+    pack_xf_kernel<true><<<(unsigned)(b * h), NT, smx, st>>>(x, stats_xf, (double2*)scratch, xf, d);
+    col_stats_kernel<<<(unsigned)(b * ((2 * w + 15) / 16)), NT, 0, st>>>((const double2*)scratch, stats_yf, d);
+    ++launches;
+  } else {
+    pack_xf_kernel<false><<<(unsigned)(b * h), NT, smx, st>>>(x, nullptr, nullptr, xf, d);
+  }
   const int chunks = (hp + yc - 1) / yc;
-  pack_yf_kernel<<<(unsigned)(b * ((w + 7) / 8) * chunks), NT, smy, (cudaStream_t)stream>>>(x, stats_yf, yf, d, yc);
-  return check_launch("planes_pack", 2);
+  pack_yf_kernel<<<(unsigned)(b * ((w + 7) / 8) * chunks), NT, smy, st>>>(x, stats_yf, yf, d, yc);
+  return check_launch("planes_pack", launches);
 }
 
 extern "C" int b2s_planes_unpack(const float* uxf, const float* uyf, const float* stats_xf, const float* stats_yf, float* out, int b, int t, int h,

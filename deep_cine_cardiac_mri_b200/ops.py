@@ -249,21 +249,23 @@ def _pad16(n: int):
 
 def raw_planes_pack(x, normalise: bool = True, pad: bool = True):
     """x (b,t,h,w,2) -> (xf (b*h,2,wp,tp), yf (b*w,2,hp,tp), ctx): the NCHW inputs of the x-f / y-f U-Nets
-    (varnet.py:215-216 + NormUnet.complex_to_chan_dim / norm / pad, norm_unet.py:48-86) in three launches.
+    (varnet.py:215-216 + NormUnet.complex_to_chan_dim / norm / pad, norm_unet.py:48-86) in three launches (x is read twice).
     `ctx` carries the statistics and pad sizes for raw_planes_unpack."""
     _need_cuda(x)
     x = _f32c(x)
     b, t, h, w, _ = x.shape
     (hp, ph0), (wp, pw0), (tp, pt0) = (_pad16(h), _pad16(w), _pad16(t)) if pad else ((h, 0), (w, 0), (t, 0))
-    sxf = syf = None
+    sxf = syf = scratch = None
+    nbytes = 0
     if normalise:
         sxf = torch.empty(b * h, 2, 2, dtype=torch.float32, device=x.device)
         syf = torch.empty(b * w, 2, 2, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib().b2s_planes_stats(_p(x), _p(sxf), _p(syf), b, t, h, w, _stream()), "planes_stats")
+        nbytes = int(_lib.lib().b2s_planes_scratch_bytes(b, t, h, w))
+        scratch = torch.empty(max(nbytes, 16) // 8, dtype=torch.float64, device=x.device)
     xf = torch.empty(b * h, 2, wp, tp, dtype=torch.float32, device=x.device)
     yf = torch.empty(b * w, 2, hp, tp, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().b2s_planes_pack(_p(x), _p(sxf), _p(syf), _p(xf), _p(yf), b, t, h, w, hp, wp, tp, ph0, pw0, pt0, _stream()),
-               "planes_pack")
+    _lib.check(_lib.lib().b2s_planes_pack(_p(x), _p(sxf), _p(syf), _p(xf), _p(yf), b, t, h, w, hp, wp, tp, ph0, pw0, pt0,
+                                          _p(scratch), nbytes, _stream()), "planes_pack")
     return xf, yf, (sxf, syf, (b, t, h, w, hp, wp, tp, ph0, pw0, pt0))
 
 

@@ -157,10 +157,14 @@ int b2s_temporal_post(const float* x, const float* mean, float* out, int b, int 
  * x (b,t,h,w,2).  stats_xf (b*h,2,2) / stats_yf (b*w,2,2) = {mean, unbiased std} of the real and imaginary parts of
  * every x-f plane (b,y) over (t,x) and every y-f plane (b,x) over (t,y) — NormUnet.norm's groups. */
 int b2s_planes_stats(const float* x, float* stats_xf, float* stats_yf, int b, int t, int h, int w, void* stream);
-/* xf (b*h,2,wp,tp), yf (b*w,2,hp,tp): the U-Nets' NCHW inputs, (x - mean)/std where statistics are given (both or
- * neither), zero-padded: plane row r holds image column/row r - pw0 / r - ph0, plane column q holds frame q - pt0. */
-int b2s_planes_pack(const float* x, const float* stats_xf, const float* stats_yf, float* xf, float* yf,
-                    int b, int t, int h, int w, int hp, int wp, int tp, int ph0, int pw0, int pt0, void* stream);
+/* xf (b*h,2,wp,tp), yf (b*w,2,hp,tp): the U-Nets' NCHW inputs, zero-padded: plane row r holds image column/row
+ * r - pw0 / r - ph0, plane column q holds frame q - pt0.  stats_xf / stats_yf both non-NULL: OUTPUTS, the group statistics
+ * are computed here (as b2s_planes_stats) and the planes are (x - mean)/std; `scratch` >= b2s_planes_scratch_bytes bytes,
+ * 16-byte aligned.  Both NULL: bare permutation (cinenet.py:193-196), no scratch. */
+size_t b2s_planes_scratch_bytes(int b, int t, int h, int w);
+int b2s_planes_pack(const float* x, float* stats_xf, float* stats_yf, float* xf, float* yf,
+                    int b, int t, int h, int w, int hp, int wp, int tp, int ph0, int pw0, int pt0,
+                    void* scratch, size_t scratch_bytes, void* stream);
 /* out (b,t,h,w,2) = 0.5 * (unnorm(unpad(uxf)) + unnorm(unpad(uyf))) from the U-Net outputs (same layouts as above). */
 int b2s_planes_unpack(const float* uxf, const float* uyf, const float* stats_xf, const float* stats_yf, float* out,
                       int b, int t, int h, int w, int hp, int wp, int tp, int ph0, int pw0, int pt0, void* stream);

@@ -491,10 +491,12 @@ def _torch_ref_ops():
     return fft2c, ifft2c, cmul, conj
 
 
-@pytest.mark.parametrize("hw", [(200, 200), (12, 10)])
+@pytest.mark.parametrize("hw", [(200, 200), (12, 10), (256, 256), (200, 200, 2, 15, 10)])
 def test_autograd_matches_torch_reference(ops, hw):
-    h, w = hw
-    b, t, c = 1, 2, 3
+    """Gradients of a reduce -> expand+DC -> masked-reduce chain w.r.t. image, sens maps, both k-spaces and lambda against
+    eager torch + cuFFT (test-only restatement): both fused plan sizes, a generic size, and config A's coil/frame counts."""
+    h, w = hw[:2]
+    b, t, c = hw[2:] if len(hw) > 2 else (1, 2, 3)
     fft2c, ifft2c, cmul, conj = _torch_ref_ops()
     cs = G.sense_case(77, b, t, c, h, w)
     mask = cu(cs["mask"])

@@ -252,6 +252,13 @@ def test_plane_pack_unpack_against_reference_normunet_glue(rec, shape):
         want.append(zz); keep.append((mean, std, pads))
     xf, yf, ctx = ops.raw_planes_pack(x, normalise=True, pad=True)
     assert xf.shape == want[0].shape and yf.shape == want[1].shape
+    # the statistics: fused into the pack kernels == the stand-alone entry point == NormUnet.norm's mean / std
+    from deep_cine_cardiac_mri_b200 import _lib
+    sx = torch.empty(b * h, 2, 2, device="cuda"); sy = torch.empty(b * w, 2, 2, device="cuda")
+    _lib.check(_lib.lib().b2s_planes_stats(ops._p(x), ops._p(sx), ops._p(sy), b, t, h, w, ops._stream()), "planes_stats")
+    for got_s, alone, (mean, std, _) in zip(ctx[:2], (sx, sy), keep):
+        assert relmax(got_s, alone) <= 1e-6
+        assert relmax(got_s[..., 0], mean.view(-1, 2)) <= 1e-6 and relmax(got_s[..., 1], std.view(-1, 2)) <= 1e-6
     assert relmax(xf, want[0]) <= 2e-6 and relmax(yf, want[1]) <= 2e-6
     # the way back: feed "U-Net outputs" u (a fixed pointwise function of the inputs) through both paths
     f = lambda z: torch.tanh(z) * 1.5 + 0.25 * z                                       # noqa: E731
