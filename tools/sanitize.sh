@@ -18,6 +18,16 @@ for (b, t, c, h, w) in ((1, 2, 2, 200, 200), (1, 1, 2, 256, 256), (1, 2, 3, 18, 
             ops.raw_sens_expand(img, s, mode, ref, m, v)
         if ops.normal_op_supported(h, w):
             ops.raw_normal_op(x, s, m, v)
+            ops.raw_normal_dc(x, s, m, v, s.pow(2).sum(dim=(1, 4)).contiguous(), img)
+        for fam in ("half", "packed"):          # both kernel families of the fused plan sizes
+            ops.set_fused_path(fam)
+            ops.raw_sens_expand(img, s, 2, ref, m, v); ops.raw_sens_expand(img, s, 0, ref, m, v); ops.raw_sens_reduce(k, s)
+        ops.set_fused_path(None)
+        for norm, pad in ((True, True), (False, False)):   # regulariser-side plane glue
+            xf, yf, ctx = ops.raw_planes_pack(x, norm, pad)
+            ops.raw_planes_unpack(xf, yf, ctx)
+    if ops.normal_op_supported(200, 36) and h == 200:
+        ops.raw_normal_op(x[..., :36, :].contiguous(), s[..., :36, :].contiguous(), m, v)      # run-time width plan
     if h >= 7 and w >= 7:
         a = torch.rand(b, 1, t, h, w, device=dev, generator=g).requires_grad_(True); bb = torch.rand(b, 1, t, h, w, device=dev, generator=g)
         metrics.ssim_loss(a, bb).backward()

@@ -40,7 +40,8 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "dram__bytes_read.su
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
-md = [f"# ncu --set full summary, {tag} (B200, tools/prof_target.py: b4 t15 c10 200x200, K = 192 MB)\n",
+nb_ = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+md = [f"# ncu --set full summary, {tag} (B200, tools/prof_target.py: b{nb_} t15 c10 200x200, K = {48 * nb_} MB)\n",
       "`ncu --set full --clock-control none --import-source on -k regex:fft2_ -s 6 -c 3` (cold-cache, serialised: durations are a little",
       "longer than the CUDA-event numbers of bench.py).  The raw .ncu-rep stays in gpurun_out/ (scratch).\n"]
 traffic = {}
@@ -54,9 +55,11 @@ for r in rows[2:]:
     t = float(r[hdr.index("dram__bytes_read.sum")]) * f[units[hdr.index("dram__bytes_read.sum")]] + \
         float(r[hdr.index("dram__bytes_write.sum")]) * f[units[hdr.index("dram__bytes_write.sum")]]
     md.append(f"| **dram read + write** | {t / 1e6:.1f} | MB per launch |")
-    if "EpiKspace" in name: traffic.update(sens_expand_dc_dram_bytes_per_launch=t, sens_expand_dc_algorithmic_bytes=416000000)
-    if "EpiReduce" in name: traffic.update(sens_reduce_dram_bytes_per_launch=t, sens_reduce_algorithmic_bytes=224000000)
-    if "EpiPlain" in name: traffic.update(fft2c_dram_bytes_per_launch=t, fft2c_algorithmic_bytes=384000000)
+    nb = int(sys.argv[4]) if len(sys.argv) > 4 else 4          # slices per launch of the capture (tools/prof_target.py argument)
+    if "EpiDCStage" in name or "EpiKspace<200, 200, 2>" in name: traffic.update(sens_expand_dc_dram_bytes_per_launch=t, sens_expand_dc_algorithmic_bytes=104000000 * nb)
+    if "EpiReduce" in name: traffic.update(sens_reduce_dram_bytes_per_launch=t, sens_reduce_algorithmic_bytes=56000000 * nb)
+    if "EpiPlain" in name: traffic.update(fft2c_dram_bytes_per_launch=t, fft2c_algorithmic_bytes=96000000 * nb)
+    if "normal_warp" in name: traffic.update(normal_op_dram_bytes_per_launch=t, normal_op_algorithmic_bytes=12800000 * nb)
 traffic["source"] = f"ncu --set full, profiles/{tag}_ncu_full_summary.md"
 (prof / f"{tag}_ncu_full_summary.md").write_text("\n".join(md) + "\n")
 json.dump(traffic, open(prof / f"{tag}_traffic.json", "w"), indent=1)
