@@ -49,6 +49,7 @@ SIGNATURES = {
     "b2s_planes_unpack": [_p, _p, _p, _p, _p] + [_i] * 10 + [_p],
     "b2s_normal_op": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2s_normal_dc": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "b2s_normal_dc_abs": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2s_dot": [_p, _p, _p, _i64, _p, _p],
     "b2s_axpy_ratio": [_p, _p, _p, _p, _f, _i64, _p],
     "b2s_xpay_ratio": [_p, _p, _p, _p, _i64, _p],

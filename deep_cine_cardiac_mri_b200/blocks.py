@@ -155,11 +155,14 @@ def _varnet_forward_image_domain(self, masked_kspace, mask, sens_maps):
     ssq = F.complex_abs_sq(s5).sum(dim=1).contiguous()                               # (b,h,w)  sum_c |S_c|^2
     bref = ops.raw_sens_reduce(mk, s5, ops.REDUCE_MASK, False, m8, None, 1)          # A^H M ref
     img = ops.raw_sens_reduce(mk, s5, ops.REDUCE_PLAIN, False, None, None, 1)        # cascade 0 starts from k = ref
-    for cascade in self.cascades:
+    n = len(self.cascades)
+    if n == 0:
+        return F.complex_abs(img)
+    for i, cascade in enumerate(self.cascades):
         model_out = _varnet_regularise(cascade, img.unsqueeze(2))
         v = cascade.Softplus(cascade.lambda_reg).detach().reshape(1).to(dtype=torch.float32)
-        img = ops.raw_normal_dc(ops._f32c(model_out.squeeze(2)), s5, m8, v, ssq, bref)
-    return F.complex_abs(img)
+        img = ops.raw_normal_dc(ops._f32c(model_out.squeeze(2)), s5, m8, v, ssq, bref, magnitude=(i == n - 1))   # last: |.| fused
+    return img
 
 
 def varnet_forward(self, masked_kspace: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:

@@ -14,7 +14,7 @@ template <class P> static int launch_warp(const NormalArgs& a, long long items, 
 
 static int launch_normal(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out, int mode,
                          const float* ssq, const float* bref, int b, int t, int c, int h, int w, void* stream) {
-  if (!x || !sens || !mask || !v || !out || b < 0 || t < 0 || c < 0 || (mode == 1 && (!ssq || !bref)))
+  if (!x || !sens || !mask || !v || !out || b < 0 || t < 0 || c < 0 || (mode >= 1 && (!ssq || !bref)))
     return fail(B2S_EINVAL, "b2s_normal_op: bad argument");
   NormalArgs a; a.x = (const cfloat*)x; a.sens = (const cfloat*)sens; a.mask = mask; a.vptr = v; a.out = (cfloat*)out;
   a.T = t; a.C = c; a.W = w; a.mode = mode; a.ssq = ssq; a.bref = (const cfloat*)bref;
@@ -36,4 +36,9 @@ extern "C" int b2s_normal_op(const float* x, const float* sens, const uint8_t* m
 extern "C" int b2s_normal_dc(const float* x, const float* sens, const uint8_t* mask, const float* v, const float* ssq,
                              const float* bref, float* out, int b, int t, int c, int h, int w, void* stream) {
   return launch_normal(x, sens, mask, v, out, 1, ssq, bref, b, t, c, h, w, stream);
+}
+
+extern "C" int b2s_normal_dc_abs(const float* x, const float* sens, const uint8_t* mask, const float* v, const float* ssq,
+                                 const float* bref, float* out_abs, int b, int t, int c, int h, int w, void* stream) {
+  return launch_normal(x, sens, mask, v, out_abs, 2, ssq, bref, b, t, c, h, w, stream);
 }

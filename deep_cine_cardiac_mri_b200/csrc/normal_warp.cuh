@@ -38,6 +38,8 @@ namespace b2s {
 // mode 1: out = ssq . x - eta (A^H M A x - bref)        (one VarNet cascade in the image domain:
 //         A^H[ DC(A x, ref) ] with ssq = sum_c |S_c|^2, bref = A^H ref, eta = v/(1+v); varnet.py:253-282
 //         followed by the next cascade's / the model's sens_reduce, varnet.py:150-151,253)
+// mode 2: as mode 1, but the LAST cascade of an inference: writes |.| (complex_abs of the final sens_reduce, varnet.py:150-151)
+//         as one float per pixel into `out` viewed as float (b,t,h,w)
 struct NormalArgs {
   const cfloat* x; const cfloat* sens; const uint8_t* mask; const float* vptr; cfloat* out;
   int T, C, W;
@@ -210,12 +212,15 @@ B2S_HD void nw_finish(const NormalArgs& a, const cfloat* ws, long long bt, int x
   } else {
     const float* dp = a.ssq + (bt / a.T) * hw + pix0;
     const cfloat* bp = a.bref + bt * hw + pix0;
+    float* mp = reinterpret_cast<float*>(a.out) + bt * hw + pix0;
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const cfloat xv = ws[P::X_OFF + 32 * k + lane];
       const float d = dp[(size_t)k * 8 * w];
       const cfloat br = bp[(size_t)k * 8 * w];
-      op[(size_t)k * 8 * w] = make_c(d * xv.x - eta * (accr[k] - br.x), d * xv.y - eta * (acci[k] - br.y));
+      const float re = d * xv.x - eta * (accr[k] - br.x), im = d * xv.y - eta * (acci[k] - br.y);
+      if (a.mode == 1) op[(size_t)k * 8 * w] = make_c(re, im);
+      else mp[(size_t)k * 8 * w] = sqrtf(re * re + im * im);           // complex_abs, utils/math.py:41-56
     }
   }
 }

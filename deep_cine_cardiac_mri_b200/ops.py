@@ -226,10 +226,17 @@ def raw_normal_op(x, sens, mask_u8, v):
     return out
 
 
-def raw_normal_dc(x, sens, mask_u8, v, ssq, bref):
-    """One image-domain VarNet DC cascade: ssq*x - v/(1+v) (A^H M A x - bref)  (inference path, h == 200)."""
+def raw_normal_dc(x, sens, mask_u8, v, ssq, bref, magnitude: bool = False):
+    """One image-domain VarNet DC cascade: ssq*x - v/(1+v) (A^H M A x - bref)  (inference path, see normal_op_supported).
+    `magnitude=True`: the last cascade - returns |.| as (b,t,h,w), the final complex_abs(sens_reduce(.)) of
+    VarNet.forward (varnet.py:150-151) fused into the same launch."""
     _need_cuda(x, sens, mask_u8, v, ssq, bref)
     b, t, h, w, _ = x.shape
+    if magnitude:
+        out = torch.empty(b, t, h, w, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().b2s_normal_dc_abs(_p(x), _p(sens), _p(mask_u8), _p(v), _p(ssq), _p(bref), _p(out), b, t,
+                                                sens.shape[1], h, w, _stream()), "normal_dc_abs")
+        return out
     out = torch.empty_like(x)
     _lib.check(_lib.lib().b2s_normal_dc(_p(x), _p(sens), _p(mask_u8), _p(v), _p(ssq), _p(bref), _p(out), b, t,
                                         sens.shape[1], h, w, _stream()), "normal_dc")

@@ -106,13 +106,15 @@ def varnet_hot_path_image_domain(masked_kspace: torch.Tensor, mask: torch.Tensor
     # cascade 0 starts from k = ref, i.e. from A^H k with NO mask (varnet.py:253), exactly like varnet_hot_path and the
     # reference; equal to bref only when the unsampled rows of the input really are zero
     img = ops.raw_sens_reduce(ops._f32c(masked_kspace), s5, ops.REDUCE_PLAIN, False, None, None, 1)
+    if n_cascades == 0:
+        return F.complex_abs(img)
     for i in range(n_cascades):
         x, mean = ops.raw_temporal_pre(img, xf)
         if regulariser is not None:
             x = regulariser(x.unsqueeze(2)).squeeze(2).contiguous()
         model_out = ops.raw_temporal_post(x, mean, xf)
-        img = ops.raw_normal_dc(model_out, s5, m8, vs[i], ssq, bref)
-    return F.complex_abs(img)
+        img = ops.raw_normal_dc(model_out, s5, m8, vs[i], ssq, bref, magnitude=(i == n_cascades - 1))   # last: |A^H k| fused
+    return img
 
 
 def cinenet_hot_path(masked_kspace: torch.Tensor, mask: torch.Tensor, sens_maps: torch.Tensor,

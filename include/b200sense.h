@@ -181,6 +181,10 @@ int b2s_normal_op(const float* x, const float* sens, const uint8_t* mask, const 
  *   sens_reduce of cascade n+1 (varnet.py:253) / of VarNet.forward (varnet.py:150-151). */
 int b2s_normal_dc(const float* x, const float* sens, const uint8_t* mask, const float* v, const float* ssq,
                   const float* bref, float* out, int b, int t, int c, int h, int w, void* stream);
+/* The last cascade of an inference with the final magnitude fused in: out_abs (b,t,h,w) = | b2s_normal_dc(...) |,
+ * i.e. complex_abs(sens_reduce(kspace_pred)) of VarNet.forward (varnet.py:150-151, utils/math.py:41-56). */
+int b2s_normal_dc_abs(const float* x, const float* sens, const uint8_t* mask, const float* v, const float* ssq,
+                      const float* bref, float* out_abs, int b, int t, int c, int h, int w, void* stream);
 /* CG scalar/vector kernels with alpha, beta kept in device memory (no .item() syncs):
  * dot: out[0] = <a,b> over n floats (deterministic two-stage; scratch >= 1024 floats) */
 int b2s_dot(const float* a, const float* b, float* out, int64_t n, float* scratch, void* stream);

@@ -179,6 +179,9 @@ def test_emulated_warp_private_normal_operator(emu, h, w, fixed):
     want = O.sens_reduce(O.dc_blend(O.sens_expand(d["img"], d["sens"]), ref_m, d["mask"], 0.8), d["sens"])
     assert emu.emu_normal_warp(P(cs["img"]), P(cs["sens"]), P(cs["mask"]), P(v), P(ssq), P(bref), P(out), 1, b, t, c, h, w, fixed) == 0
     assert rel(out, want) <= 1e-6
+    mag = np.empty((b, t, h, w), np.float32)                  # mode 2: the final magnitude fused in (varnet.py:150-151)
+    assert emu.emu_normal_warp(P(cs["img"]), P(cs["sens"]), P(cs["mask"]), P(v), P(ssq), P(bref), P(mag), 2, b, t, c, h, w, fixed) == 0
+    assert rel(mag, O.complex_abs(want[:, :, 0])) <= 1e-6
 
 
 # ------------------------------------------------------------------ host logic

@@ -176,6 +176,17 @@ def test_normal_op_and_cg(ops, tag):
     # composed path (used when sens needs grad / other sizes) agrees too
     comp = ops.sens_reduce(ops.sens_expand(img, sens, ops.EXPAND_MASK, mask=mask), sens) + v * img.squeeze(2)
     assert rel(comp.unsqueeze(2), want) <= TOL
+    # image-domain cascade (b2s_normal_dc) and its last-cascade form with the final magnitude fused in (b2s_normal_dc_abs)
+    b_, t_, c_, h_, w_ = CASES[tag]
+    vd = torch.tensor([v], device="cuda")
+    m8 = ops._mask_u8(mask, b_, t_, h_)
+    ref_m = O.apply_mask(d["ref"], d["mask"])
+    bref = cu(O.sens_reduce(ref_m, d["sens"], keepdim=False).astype(np.float32))
+    ssq = cu((d["sens"] ** 2).sum(axis=(2, 5))[:, 0].astype(np.float32))
+    want_dc = O.sens_reduce(O.dc_blend(O.sens_expand(d["img"], d["sens"]), ref_m, d["mask"], v), d["sens"], keepdim=False)
+    x5, s5 = img.squeeze(2).contiguous(), sens.squeeze(1).contiguous()
+    assert rel(ops.raw_normal_dc(x5, s5, m8, vd, ssq, bref), want_dc) <= TOL
+    assert rel(ops.raw_normal_dc(x5, s5, m8, vd, ssq, bref, magnitude=True), O.complex_abs(want_dc)) <= TOL
     import types
     blk = types.SimpleNamespace(Softplus=torch.nn.Softplus(1.), lambda_reg=torch.tensor([float(cs["lam"])], device="cuda"))
     rhs = O.sens_reduce(O.apply_mask(d["ref"], d["mask"]), d["sens"]) + v * d["img"]
