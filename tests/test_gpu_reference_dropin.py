@@ -231,7 +231,7 @@ def test_xpdnet_block_bodies_match_reference(rec):
 # ------------------------------------------------------------------------------------------------------------------ #
 # regulariser-side layout glue: plane packing around the REAL NormUnet / Unet
 # ------------------------------------------------------------------------------------------------------------------ #
-@pytest.mark.parametrize("shape", [(2, 15, 200, 200), (1, 7, 24, 40), (1, 30, 256, 256), (1, 16, 32, 48)])
+@pytest.mark.parametrize("shape", [(2, 15, 200, 200), (1, 7, 24, 40), (1, 30, 256, 256), (1, 16, 32, 48), (1, 3, 18, 36), (2, 5, 10, 12), (1, 17, 20, 6)])
 def test_plane_pack_unpack_against_reference_normunet_glue(rec, shape):
     """b2s_planes_stats / pack / unpack against the reference's own glue: the permute/view pairs of
     VarNetBlock.xfyf_transform (varnet.py:215-216, 228-232) and NormUnet.complex_to_chan_dim / norm / pad / unpad /
