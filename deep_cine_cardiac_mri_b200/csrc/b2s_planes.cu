@@ -141,12 +141,20 @@ __global__ void __launch_bounds__(NT) pack_xf_kernel(const float* __restrict__ x
   }
   const int plane = d.WP * d.TP;
   float* o = out + (size_t)by * 2 * plane;
-  for (int i = threadIdx.x; i < 2 * plane; i += NT) {
-    const int ch = i / plane, r = i - ch * plane, xp = r / d.TP, tp = r - xp * d.TP;
-    const int xx = xp - d.pw0, t = tp - d.pt0;
-    float v = 0.f;
-    if (xx >= 0 && xx < d.W && t >= 0 && t < d.T) { v = tile[t * pitch + 2 * xx + ch]; if (NORM) v = (v - ms[ch * 2]) / ms[ch * 2 + 1]; }
-    o[i] = v;
+  // a thread keeps its plane column tp and walks down the (channel, xp) rows: no divisions in the loop
+  const int tp = threadIdx.x % d.TP, r0 = threadIdx.x / d.TP, rstep = NT / d.TP, t = tp - d.pt0;
+  const bool tin = t >= 0 && t < d.T && r0 < rstep;          // (NT % TP != 0: the last partial group of threads idles)
+  if (rstep > 0) {
+    for (int ch = 0; ch < 2; ++ch) {
+      const float mean = NORM ? ms[ch * 2] : 0.f, sd = NORM ? ms[ch * 2 + 1] : 1.f;
+      for (int xp = r0; xp < d.WP; xp += rstep) {
+        if (r0 >= rstep) break;
+        const int xx = xp - d.pw0;
+        float v = 0.f;
+        if (tin && xx >= 0 && xx < d.W) { v = tile[t * pitch + 2 * xx + ch]; if (NORM) v = (v - mean) / sd; }
+        o[(size_t)ch * plane + xp * d.TP + tp] = v;
+      }
+    }
   }
 }
 
@@ -179,32 +187,41 @@ __global__ void __launch_bounds__(NT) pack_yf_kernel(const float* __restrict__ x
   const int yp0 = ck * YC, nyp = min(YC, d.HP - yp0);
   const int e = threadIdx.x & 15, seg = threadIdx.x >> 4;
   const int col = x0 + (e >> 1);
-  for (int base = seg; base < d.T * nyp; base += (NT / 16) * U) {
-    float v[U];
+  for (int t = 0; t < d.T; ++t) {
+    const float* pt = x + (((size_t)b * d.T + t) * d.H) * d.W * 2 + (size_t)col * 2 + (e & 1);
+    for (int yl0 = seg; yl0 < nyp; yl0 += (NT / 16) * U) {
+      float v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int s = base + u * (NT / 16), t = s / nyp, yl = s - t * nyp, y = yp0 + yl - d.ph0;
-      v[u] = (s < d.T * nyp && y >= 0 && y < d.H && col < d.W) ? x[((((size_t)b * d.T + t) * d.H + y) * d.W + col) * 2 + (e & 1)] : 0.f;
-    }
+      for (int u = 0; u < U; ++u) {
+        const int yl = yl0 + u * (NT / 16), y = yp0 + yl - d.ph0;
+        v[u] = (yl < nyp && y >= 0 && y < d.H && col < d.W) ? pt[(size_t)y * d.W * 2] : 0.f;
+      }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int s = base + u * (NT / 16);
-      if (s < d.T * nyp) tile[s * 17 + e] = v[u];
+      for (int u = 0; u < U; ++u) {
+        const int yl = yl0 + u * (NT / 16);
+        if (yl < nyp) tile[(t * nyp + yl) * 17 + e] = v[u];
+      }
     }
   }
   __syncthreads();
-  const int plane = d.HP * d.TP, blk = nyp * d.TP;
-  for (int i = threadIdx.x; i < 16 * blk; i += NT) {
-    const int ee = i / blk, r = i - ee * blk, yl = r / d.TP, tp = r - yl * d.TP;
-    const int c2 = x0 + (ee >> 1), ch = ee & 1;
-    if (c2 >= d.W) continue;
-    const int y = yp0 + yl - d.ph0, t = tp - d.pt0;
-    float v = 0.f;
-    if (y >= 0 && y < d.H && t >= 0 && t < d.T) {
-      v = tile[(t * nyp + yl) * 17 + ee];
-      if (stats) { const float* st = stats + (((size_t)b * d.W + c2) * 2 + ch) * 2; v = (v - st[0]) / st[1]; }
+  const int plane = d.HP * d.TP;
+  // a thread keeps its plane column tp and walks down the rows of one (column, channel) block after the other
+  const int tp = threadIdx.x % d.TP, r0 = threadIdx.x / d.TP, rstep = NT / d.TP, t = tp - d.pt0;
+  const bool tin = t >= 0 && t < d.T;
+  if (rstep > 0 && r0 < rstep) {
+    for (int ee = 0; ee < 16; ++ee) {
+      const int c2 = x0 + (ee >> 1), ch = ee & 1;
+      if (c2 >= d.W) break;
+      float mean = 0.f, sd = 1.f;
+      if (stats) { const float* st = stats + (((size_t)b * d.W + c2) * 2 + ch) * 2; mean = st[0]; sd = st[1]; }
+      float* o = out + ((size_t)(b * d.W + c2) * 2 + ch) * plane + (size_t)yp0 * d.TP + tp;
+      for (int yl = r0; yl < nyp; yl += rstep) {
+        const int y = yp0 + yl - d.ph0;
+        float v = 0.f;
+        if (tin && y >= 0 && y < d.H) { v = tile[(t * nyp + yl) * 17 + ee]; if (stats) v = (v - mean) / sd; }
+        o[(size_t)yl * d.TP] = v;
+      }
     }
-    out[((size_t)(b * d.W + c2) * 2 + ch) * plane + (size_t)(yp0 + yl) * d.TP + tp] = v;
   }
 }
 
@@ -223,21 +240,26 @@ __global__ void __launch_bounds__(NT) unpack_kernel(const float* __restrict__ ux
   const int planex = d.WP * d.TP, planey = d.HP * d.TP;
   const float* px = uxf + (size_t)by * 2 * planex;
   {
-    const int na = 2 * planex, nb = 2 * d.W * d.TP;
-    const float* py = uyf + (size_t)(b * d.W) * 2 * planey + (size_t)(y + d.ph0) * d.TP;
-    for (int base = threadIdx.x; base < na + nb; base += NT * U) {
-      float v[U];
+    // a thread keeps its plane column tp: rows of the x-f plane (2 WP of them), then the TP-float runs of the y-f planes
+    // (2 W of them), U loads in flight, no divisions in the loops
+    const int tp = threadIdx.x % d.TP, r0 = threadIdx.x / d.TP, rstep = NT / d.TP;
+    const int na = 2 * d.WP, nb = 2 * d.W;
+    const float* py = uyf + (size_t)(b * d.W) * 2 * planey + (size_t)(y + d.ph0) * d.TP + tp;
+    if (r0 < rstep) {
+      for (int base = r0; base < na + nb; base += rstep * U) {
+        float v[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = base + u * NT;
-        if (i < na) v[u] = px[i];
-        else if (i < na + nb) { const int k = i - na, xc = k / d.TP, tp = k - xc * d.TP; v[u] = py[(size_t)xc * planey + tp]; }   // xc = x * 2 + ch
-      }
+        for (int u = 0; u < U; ++u) {
+          const int r = base + u * rstep;
+          if (r < na) v[u] = px[r * d.TP + tp];
+          else if (r < na + nb) v[u] = py[(size_t)(r - na) * planey];                 // r - na = x * 2 + ch
+        }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = base + u * NT;
-        if (i < na) A[(i / d.TP) * tpp + i % d.TP] = v[u];
-        else if (i < na + nb) { const int k = i - na, xc = k / d.TP, tp = k - xc * d.TP; Bf[xc * tpp + tp] = v[u]; }
+        for (int u = 0; u < U; ++u) {
+          const int r = base + u * rstep;
+          if (r < na) A[r * tpp + tp] = v[u];
+          else if (r < na + nb) Bf[(r - na) * tpp + tp] = v[u];
+        }
       }
     }
   }
@@ -260,7 +282,7 @@ __global__ void __launch_bounds__(NT) unpack_kernel(const float* __restrict__ ux
 }
 
 int check_dims(const char* what, int b, int t, int h, int w, int hp, int wp, int tp, int ph0, int pw0, int pt0) {
-  if (b < 0 || t <= 0 || h <= 0 || w <= 0 || hp < h || wp < w || tp < t || ph0 < 0 || pw0 < 0 || pt0 < 0 || ph0 + h > hp || pw0 + w > wp || pt0 + t > tp)
+  if (b < 0 || t <= 0 || h <= 0 || w <= 0 || hp < h || wp < w || tp < t || tp > NT || ph0 < 0 || pw0 < 0 || pt0 < 0 || ph0 + h > hp || pw0 + w > wp || pt0 + t > tp)
     return fail(B2S_EINVAL, what);
   return B2S_OK;
 }
