@@ -217,7 +217,7 @@ def raw_dc_blend_bwd(g, out, ref, mask_u8, v, want_gk, want_gref, want_gv):
 
 
 def raw_normal_op(x, sens, mask_u8, v):
-    """x (b,t,h,w,2) -> A^H M A x + v x (on-chip kernel; h == 200)."""
+    """x (b,t,h,w,2) -> A^H M A x + v x (on-chip kernel, csrc/normal_warp.cuh; see normal_op_supported)."""
     _need_cuda(x, sens, mask_u8, v)
     b, t, h, w, _ = x.shape
     out = torch.empty_like(x)
