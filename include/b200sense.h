@@ -52,6 +52,11 @@ extern "C" {
  * Costs one extra K-sized round trip; needs b*t*c*h*w*8 bytes of scratch for every shape. */
 #define B2S_REDUCE_DETERMINISTIC 0x10
 
+/* State.  Every operator entry point below is a pure function of its arguments (device pointers, sizes, stream): the library
+ * keeps no per-call or per-tensor state and may be called concurrently from several host threads on different streams.
+ * The only mutable process-wide settings are the two launch-configuration knobs b2s_set_sm_reserve and b2s_set_fused_path
+ * (atomics, read once per launch; meant to be set at start-up, they never change results, only which SMs / which kernel
+ * family a launch uses), the launch counter, and the thread-local text of b2s_last_error. */
 int b2s_version(void);
 const char* b2s_last_error(void);
 /* number of CUDA kernels this library has launched so far (host-side counter; reset != 0 zeroes it) */
