@@ -50,6 +50,10 @@ SIGNATURES = {
     "b2s_normal_op": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2s_normal_dc": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b2s_normal_dc_abs": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "b2s_normal_op_dot": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "b2s_cg_blocks": [_i64],
+    "b2s_cg_update": [_p, _p, _p, _p, _p, _i, _p, _p, _i64, _p],
+    "b2s_cg_direction": [_p, _p, _p, _p, _p, _i64, _p],
     "b2s_dot": [_p, _p, _p, _i64, _p, _p],
     "b2s_axpy_ratio": [_p, _p, _p, _p, _f, _i64, _p],
     "b2s_xpay_ratio": [_p, _p, _p, _p, _i64, _p],

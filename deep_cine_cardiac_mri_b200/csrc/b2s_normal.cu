@@ -13,11 +13,11 @@ template <class P> static int launch_warp(const NormalArgs& a, long long items, 
 }
 
 static int launch_normal(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out, int mode,
-                         const float* ssq, const float* bref, int b, int t, int c, int h, int w, void* stream) {
+                         const float* ssq, const float* bref, int b, int t, int c, int h, int w, void* stream, float* dot_part = nullptr) {
   if (!x || !sens || !mask || !v || !out || b < 0 || t < 0 || c < 0 || (mode >= 1 && (!ssq || !bref)))
     return fail(B2S_EINVAL, "b2s_normal_op: bad argument");
   NormalArgs a; a.x = (const cfloat*)x; a.sens = (const cfloat*)sens; a.mask = mask; a.vptr = v; a.out = (cfloat*)out;
-  a.T = t; a.C = c; a.W = w; a.mode = mode; a.ssq = ssq; a.bref = (const cfloat*)bref;
+  a.T = t; a.C = c; a.W = w; a.mode = mode; a.ssq = ssq; a.bref = (const cfloat*)bref; a.dot_part = dot_part;
   if ((h != 200 && h != 256) || w % 4 != 0 || w <= 0)
     return fail(B2S_EUNSUPPORTED, "b2s_normal_op: needs h in {200, 256} and w % 4 == 0");
   const long long items = (long long)b * t * (w / 4);
@@ -41,4 +41,12 @@ extern "C" int b2s_normal_dc(const float* x, const float* sens, const uint8_t* m
 extern "C" int b2s_normal_dc_abs(const float* x, const float* sens, const uint8_t* mask, const float* v, const float* ssq,
                                  const float* bref, float* out_abs, int b, int t, int c, int h, int w, void* stream) {
   return launch_normal(x, sens, mask, v, out_abs, 2, ssq, bref, b, t, c, h, w, stream);
+}
+
+// H x together with the per-item partial sums of <x, H x> (b * t * w / 4 floats): one CG iteration needs no separate dot
+// kernel for <p, H p> (cinenet.py:159); the partials are summed in a fixed order by b2s_cg_update.
+extern "C" int b2s_normal_op_dot(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out, float* dot_partials,
+                                 int b, int t, int c, int h, int w, void* stream) {
+  if (!dot_partials) return fail(B2S_EINVAL, "b2s_normal_op_dot: null pointer");
+  return launch_normal(x, sens, mask, v, out, 0, nullptr, nullptr, b, t, c, h, w, stream, dot_partials);
 }

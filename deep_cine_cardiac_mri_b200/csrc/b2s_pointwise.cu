@@ -407,6 +407,38 @@ __global__ void xpay_ratio_kernel(float* p, const float* r, const float* num, co
   const float bta = num[0] / den[0];
   GRID_STRIDE(i, n) p[i] = r[i] + bta * p[i];
 }
+// sum of n partials in a fixed order, result broadcast to the whole block
+__device__ __forceinline__ float block_total(const float* __restrict__ part, int n) {
+  __shared__ float tot;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) tot = acc;
+  __syncthreads();
+  return tot;
+}
+// one CG iteration after d = H p (cinenet.py:159-164): alpha = rs_old / <p, d>;  x += alpha p;  r -= alpha d;  partials of <r, r>
+__global__ void cg_update_kernel(const float* __restrict__ p, const float* __restrict__ d, float* __restrict__ x, float* __restrict__ r,
+                                 const float* __restrict__ pd_part, int n_pd, const float* __restrict__ rs_old, float* __restrict__ rr_part, long long n) {
+  const float alpha = rs_old[0] / block_total(pd_part, n_pd);
+  float acc = 0.f;
+  GRID_STRIDE(i, n) {
+    x[i] = x[i] + alpha * p[i];
+    const float rn = r[i] - alpha * d[i];
+    r[i] = rn;
+    acc += rn * rn;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) rr_part[blockIdx.x] = acc;
+}
+// ... and its second half (cinenet.py:165-167): rs_new = <r, r>;  p = r + (rs_new / rs_old) p
+__global__ void cg_direction_kernel(float* __restrict__ p, const float* __restrict__ r, const float* __restrict__ rr_part, int n_rr,
+                                    const float* __restrict__ rs_old, float* __restrict__ rs_new, long long n) {
+  const float rn = block_total(rr_part, n_rr);
+  const float beta = rn / rs_old[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) rs_new[0] = rn;
+  GRID_STRIDE(i, n) p[i] = r[i] + beta * p[i];
+}
 __global__ void axpby_kernel(const float* a, const float* b, const float* v, float scale, float* out, long long n) {
   const float s = v ? v[0] * scale : scale;
   GRID_STRIDE(i, n) out[i] = a[i] + s * b[i];
@@ -626,4 +658,22 @@ extern "C" int b2s_axpby(const float* a, const float* b, const float* v, float s
   if (n == 0) return B2S_OK;
   axpby_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(a, b, v, scale, out, n);
   return check_launch("axpby_kernel");
+}
+
+// Fused CG iteration (after d = H p with the <p, d> partials of b2s_normal_op_dot): two launches instead of six
+extern "C" int b2s_cg_blocks(int64_t n) { return (int)grid_for(n, NT, 1024); }
+
+extern "C" int b2s_cg_update(const float* p, const float* d, float* x, float* r, const float* pd_partials, int n_pd, const float* rs_old,
+                             float* rr_partials, int64_t n, void* stream) {
+  if (!p || !d || !x || !r || !pd_partials || !rs_old || !rr_partials || n_pd <= 0) return fail(B2S_EINVAL, "b2s_cg_update: bad argument");
+  if (n == 0) return B2S_OK;
+  cg_update_kernel<<<grid_for(n, NT, 1024), NT, 0, (cudaStream_t)stream>>>(p, d, x, r, pd_partials, n_pd, rs_old, rr_partials, n);
+  return check_launch("cg_update_kernel");
+}
+
+extern "C" int b2s_cg_direction(float* p, const float* r, const float* rr_partials, const float* rs_old, float* rs_new, int64_t n, void* stream) {
+  if (!p || !r || !rr_partials || !rs_old || !rs_new || rs_old == rs_new) return fail(B2S_EINVAL, "b2s_cg_direction: bad argument");
+  if (n == 0) return B2S_OK;
+  cg_direction_kernel<<<grid_for(n, NT, 1024), NT, 0, (cudaStream_t)stream>>>(p, r, rr_partials, (int)grid_for(n, NT, 1024), rs_old, rs_new, n);
+  return check_launch("cg_direction_kernel");
 }

@@ -44,6 +44,7 @@ struct NormalArgs {
   const cfloat* x; const cfloat* sens; const uint8_t* mask; const float* vptr; cfloat* out;
   int T, C, W;
   int mode; const float* ssq; const cfloat* bref;
+  float* dot_part;     // mode 0, optional: dot_part[item] = sum over the item's pixels of Re<x, H x> (CG's <p, H p>, cinenet.py:159)
 };
 
 struct alignas(16) nquad { float ra, rb, ia, ib; };
@@ -193,9 +194,10 @@ B2S_HD void nw_step3(const cfloat* ws, int lane, const cfloat (&sv)[P::G], float
   }
 }
 
+// returns this lane's share of <x, H x> (mode 0; 0 otherwise)
 template <class P>
-B2S_HD void nw_finish(const NormalArgs& a, const cfloat* ws, long long bt, int x0, int lane, const float (&accr)[P::G],
-                      const float (&acci)[P::G], float v) {
+B2S_HD float nw_finish(const NormalArgs& a, const cfloat* ws, long long bt, int x0, int lane, const float (&accr)[P::G],
+                       const float (&acci)[P::G], float v) {
   constexpr int G = P::G;
   const int m = lane >> 2, xl = lane & 3;
   const int w = nw_width<P>(a);
@@ -203,11 +205,14 @@ B2S_HD void nw_finish(const NormalArgs& a, const cfloat* ws, long long bt, int x
   const long long pix0 = (long long)m * w + x0 + xl;
   cfloat* op = a.out + bt * hw + pix0;
   const float eta = v / (1.f + v);
+  float dsum = 0.f;
   if (a.mode == 0) {
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const cfloat xv = ws[P::X_OFF + 32 * k + lane];
-      op[(size_t)k * 8 * w] = make_c(accr[k] + v * xv.x, acci[k] + v * xv.y);
+      const float hr = accr[k] + v * xv.x, hi = acci[k] + v * xv.y;
+      op[(size_t)k * 8 * w] = make_c(hr, hi);
+      dsum += xv.x * hr + xv.y * hi;
     }
   } else {
     const float* dp = a.ssq + (bt / a.T) * hw + pix0;
@@ -223,6 +228,7 @@ B2S_HD void nw_finish(const NormalArgs& a, const cfloat* ws, long long bt, int x
       else mp[(size_t)k * 8 * w] = sqrtf(re * re + im * im);           // complex_abs, utils/math.py:41-56
     }
   }
+  return dsum;
 }
 
 #if defined(__CUDACC__)
@@ -271,7 +277,12 @@ __global__ void __launch_bounds__(P::NT, P::CTAS) normal_warp_kernel(const Norma
     nw_step3<P>(ws, lane, sv, accr, acci);
     __syncwarp();
   }
-  nw_finish<P>(a, ws, bt, x0, lane, accr, acci, *a.vptr);
+  float dsum = nw_finish<P>(a, ws, bt, x0, lane, accr, acci, *a.vptr);
+  if (a.dot_part) {                                       // fixed-order butterfly over the warp: bit-reproducible partials
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if (lane == 0) a.dot_part[item] = dsum;
+  }
 }
 #endif
 
@@ -300,7 +311,9 @@ void normal_warp_emulate(const NormalArgs& a, long long n_bt) {
       for (int task = 0; task < P::TASKS2; ++task) nw_step2<P>(ws, smem, task);
       for (int lane = 0; lane < 32; ++lane) nw_step3<P>(ws, lane, sv[lane], accr[lane], acci[lane]);
     }
-    for (int lane = 0; lane < 32; ++lane) nw_finish<P>(a, ws, bt, x0, lane, accr[lane], acci[lane], *a.vptr);
+    float dsum = 0.f;
+    for (int lane = 0; lane < 32; ++lane) dsum += nw_finish<P>(a, ws, bt, x0, lane, accr[lane], acci[lane], *a.vptr);
+    if (a.dot_part) a.dot_part[item] = dsum;
   }
   delete[] smem; delete[] accr; delete[] acci; delete[] sv;
 }

@@ -190,6 +190,18 @@ int b2s_normal_dc(const float* x, const float* sens, const uint8_t* mask, const 
  * i.e. complex_abs(sens_reduce(kspace_pred)) of VarNet.forward (varnet.py:150-151, utils/math.py:41-56). */
 int b2s_normal_dc_abs(const float* x, const float* sens, const uint8_t* mask, const float* v, const float* ssq,
                       const float* bref, float* out_abs, int b, int t, int c, int h, int w, void* stream);
+/* H x as b2s_normal_op, plus dot_partials[b*t*w/4]: per work item the partial sum of <x, H x> (real inner product over
+ * the float pairs) - CG's <p, H p> (cinenet.py:159) without a separate dot kernel.  Fixed summation order. */
+int b2s_normal_op_dot(const float* x, const float* sens, const uint8_t* mask, const float* v, float* out,
+                      float* dot_partials, int b, int t, int c, int h, int w, void* stream);
+/* One CG iteration after d = H p (cinenet.py:159-167) in two launches, all scalars on the device, fixed summation order:
+ *   b2s_cg_update:    alpha = rs_old / sum(pd_partials[0..n_pd));  x += alpha p;  r -= alpha d;  rr_partials[b2s_cg_blocks(n)] = partials of <r, r>
+ *   b2s_cg_direction: rs_new = sum(rr_partials);  p = r + (rs_new / rs_old) p          (n = floats per vector) */
+int b2s_cg_blocks(int64_t n);
+int b2s_cg_update(const float* p, const float* d, float* x, float* r, const float* pd_partials, int n_pd,
+                  const float* rs_old, float* rr_partials, int64_t n, void* stream);
+int b2s_cg_direction(float* p, const float* r, const float* rr_partials, const float* rs_old, float* rs_new,
+                     int64_t n, void* stream);
 /* CG scalar/vector kernels with alpha, beta kept in device memory (no .item() syncs):
  * dot: out[0] = <a,b> over n floats (deterministic two-stage; scratch >= 1024 floats) */
 int b2s_dot(const float* a, const float* b, float* out, int64_t n, float* scratch, void* stream);

@@ -136,7 +136,7 @@ extern "C" int emu_normal_warp(const float* x, const float* sens, const uint8_t*
   if ((h != 200 && h != 256) || w % 4) return 2;
   if (fixed && w != h) return 2;
   NormalArgs a; a.x = (const cfloat*)x; a.sens = (const cfloat*)sens; a.mask = mask; a.vptr = v; a.out = (cfloat*)out;
-  a.T = t; a.C = c; a.W = w; a.mode = mode; a.ssq = ssq; a.bref = (const cfloat*)bref;
+  a.T = t; a.C = c; a.W = w; a.mode = mode; a.ssq = ssq; a.bref = (const cfloat*)bref; a.dot_part = nullptr;
   const long long n = (long long)b * t;
   if (h == 200) { if (fixed) normal_warp_emulate<NormalWarpPlan<200, 200, 3, 4>>(a, n); else normal_warp_emulate<NormalWarpPlan<200, 0, 3, 4>>(a, n); }
   else          { if (fixed) normal_warp_emulate<NormalWarpPlan<256, 256, 4, 2>>(a, n); else normal_warp_emulate<NormalWarpPlan<256, 0, 4, 2>>(a, n); }

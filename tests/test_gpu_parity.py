@@ -187,6 +187,15 @@ def test_normal_op_and_cg(ops, tag):
     x5, s5 = img.squeeze(2).contiguous(), sens.squeeze(1).contiguous()
     assert rel(ops.raw_normal_dc(x5, s5, m8, vd, ssq, bref), want_dc) <= TOL
     assert rel(ops.raw_normal_dc(x5, s5, m8, vd, ssq, bref, magnitude=True), O.complex_abs(want_dc)) <= TOL
+    # H x with the fused <x, H x> partials (b2s_normal_op_dot): same H x, partials sum to the real inner product
+    from deep_cine_cardiac_mri_b200 import _lib
+    hx = torch.empty_like(x5)
+    part = torch.full((b_ * t_ * (w_ // 4),), float("nan"), device="cuda")
+    _lib.check(_lib.lib().b2s_normal_op_dot(ops._p(x5), ops._p(s5), ops._p(m8), ops._p(vd), ops._p(hx), ops._p(part), b_, t_, c_, h_, w_,
+                                            ops._stream()), "normal_op_dot")
+    assert torch.equal(hx, ops.raw_normal_op(x5, s5, m8, vd))
+    want_dot = float((d["img"][:, :, 0] * want[:, :, 0]).sum())
+    assert abs(float(part.double().sum()) - want_dot) <= 1e-5 * abs(want_dot)
     import types
     blk = types.SimpleNamespace(Softplus=torch.nn.Softplus(1.), lambda_reg=torch.tensor([float(cs["lam"])], device="cuda"))
     rhs = O.sens_reduce(O.apply_mask(d["ref"], d["mask"]), d["sens"]) + v * d["img"]
