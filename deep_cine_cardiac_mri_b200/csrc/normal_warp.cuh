@@ -194,6 +194,21 @@ B2S_HD void nw_step3(const cfloat* ws, int lane, const cfloat (&sv)[P::G], float
   }
 }
 
+// the coil sum starts at 0 (normal operator) or at -bref (image-domain cascade: A^H M A x - bref is what the epilogue needs, and
+// loading bref here puts its HBM latency behind the x / S_0 loads instead of at the end of the item)
+template <class P>
+B2S_HD void nw_init_acc(const NormalArgs& a, long long bt, int x0, int lane, float (&accr)[P::G], float (&acci)[P::G]) {
+  if (a.mode == 0) {
+#pragma unroll
+    for (int k = 0; k < P::G; ++k) { accr[k] = 0.f; acci[k] = 0.f; }
+  } else {
+    const int w = nw_width<P>(a);
+    const cfloat* bp = a.bref + (bt * P::H + (lane >> 2)) * (long long)w + x0 + (lane & 3);
+#pragma unroll
+    for (int k = 0; k < P::G; ++k) { const cfloat br = bp[(size_t)k * 8 * w]; accr[k] = -br.x; acci[k] = -br.y; }
+  }
+}
+
 // returns this lane's share of <x, H x> (mode 0; 0 otherwise)
 template <class P>
 B2S_HD float nw_finish(const NormalArgs& a, const cfloat* ws, long long bt, int x0, int lane, const float (&accr)[P::G],
@@ -216,14 +231,12 @@ B2S_HD float nw_finish(const NormalArgs& a, const cfloat* ws, long long bt, int 
     }
   } else {
     const float* dp = a.ssq + (bt / a.T) * hw + pix0;
-    const cfloat* bp = a.bref + bt * hw + pix0;
     float* mp = reinterpret_cast<float*>(a.out) + bt * hw + pix0;
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const cfloat xv = ws[P::X_OFF + 32 * k + lane];
       const float d = dp[(size_t)k * 8 * w];
-      const cfloat br = bp[(size_t)k * 8 * w];
-      const float re = d * xv.x - eta * (accr[k] - br.x), im = d * xv.y - eta * (acci[k] - br.y);
+      const float re = d * xv.x - eta * accr[k], im = d * xv.y - eta * acci[k];      // acc = A^H M A x - bref (nw_init_acc)
       if (a.mode == 1) op[(size_t)k * 8 * w] = make_c(re, im);
       else mp[(size_t)k * 8 * w] = sqrtf(re * re + im * im);           // complex_abs, utils/math.py:41-56
     }
@@ -249,19 +262,9 @@ __global__ void __launch_bounds__(P::NT, P::CTAS) normal_warp_kernel(const Norma
   const size_t hw = (size_t)P::H * w;
   const cfloat* sp = a.sens + (size_t)(bt / a.T) * a.C * hw + (size_t)(lane >> 2) * w + x0 + (lane & 3);
   nw_stage<P>(a, ws, bt, x0, lane);
-  if (a.mode != 0 && (lane & 3) == 0) {                   // warm L2 with this item's bref / ssq segments (read in nw_finish)
-    const char* bp = reinterpret_cast<const char*>(a.bref + bt * hw + (size_t)(lane >> 2) * w + x0);
-    const char* dp = reinterpret_cast<const char*>(a.ssq + (bt / a.T) * hw + (size_t)(lane >> 2) * w + x0);
-#pragma unroll
-    for (int i = 0; i < P::G; ++i) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(bp + (size_t)i * 8 * w * 8));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(dp + (size_t)i * 8 * w * 4));
-    }
-  }
   float accr[P::G], acci[P::G];
   cfloat sv[P::G];
-#pragma unroll
-  for (int k = 0; k < P::G; ++k) { accr[k] = 0.f; acci[k] = 0.f; }
+  nw_init_acc<P>(a, bt, x0, lane, accr, acci);
   __syncwarp();                                           // mask factors visible to the warp
 #pragma unroll 1
   for (int c = 0; c < a.C; ++c) {
@@ -304,7 +307,7 @@ void normal_warp_emulate(const NormalArgs& a, long long n_bt) {
     for (int lane = 0; lane < 32; ++lane) {
       sp[lane] = a.sens + (size_t)(bt / a.T) * a.C * hw + (size_t)(lane >> 2) * w + x0 + (lane & 3);
       nw_stage<P>(a, ws, bt, x0, lane);
-      for (int k = 0; k < P::G; ++k) { accr[lane][k] = 0.f; acci[lane][k] = 0.f; }
+      nw_init_acc<P>(a, bt, x0, lane, accr[lane], acci[lane]);
     }
     for (int c = 0; c < a.C; ++c) {
       for (int lane = 0; lane < 32; ++lane) { nw_step1<P>(a, ws, smem, sp[lane], lane, sv[lane]); sp[lane] += hw; }
