@@ -37,7 +37,10 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOAD = "XF-VarNet 12-cascade SENSE/DC hot path, 10-coil 15-frame 200x200 cine slices"
-CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=16, streams=2, upload_sms=4)
+# streams: the slice batch can be split over CUDA streams inside the graph (pipeline.varnet_hot_path_streams); measured
+# (tools/batch_sweep.py, profiles/r2_batch_sweep.txt): two streams win at 4 slices per step (1058 vs 1004 slices/s), one stream
+# wins from 8 slices on (16 slices: 1122 vs 1041)
+CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=16, streams=1, upload_sms=4)
 for _k, _e in (("upload_sms", "B2S_BENCH_UPLOAD_SMS"), ("streams", "B2S_BENCH_STREAMS"), ("slices_per_gpu_step", "B2S_BENCH_SLICES")):
     if os.environ.get(_e):                          # dev overrides
         CFG[_k] = int(os.environ[_e])
@@ -340,7 +343,7 @@ def run_ours(args, rank, world, local):
         #      Only the sampled k-space rows cross PCIe: the masked k-space a scanner pipeline hands over is 75 % zero rows
         #      (data/transforms.py:66-92), ops.upload_masked_kspace reads the others' neighbours straight from the pinned
         #      buffer on 4 SMs that the persistent kernels of the captured step leave free (b2s_set_sm_reserve).
-        copy_stream, comp_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        copy_stream, comp_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         ops.set_sm_reserve(CFG["upload_sms"])
 
         def e2e_fn(k_in, m_in):
@@ -349,25 +352,33 @@ def run_ours(args, rank, world, local):
             graphs = [pipeline.Graphed(e2e_fn, mk, mask, warmup=1) for _ in range(2)]   # static input buffers = the H2D targets
         torch.cuda.synchronize()
         out_host = [torch.empty((b, t, h, w), dtype=torch.float32).pin_memory() for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]    # inputs of graph s uploaded
+        done = [torch.cuda.Event() for _ in range(2)]     # graph s computed: its input buffers may be overwritten
+        freed = [torch.cuda.Event() for _ in range(2)]    # result of graph s downloaded: its output buffer may be overwritten
 
         def e2e_run(n):
+            # three streams, two graphs: the upload of step i+1 and the download of step i-1 run beside the compute of step i
             for i in range(n):
                 s = i % 2
                 with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(freed[s])
+                    copy_stream.wait_event(done[s])
                     graphs[s].inputs[1].copy_(mask_host, non_blocking=True)
                     ops.upload_masked_kspace(mk_host, graphs[s].inputs[1], out=graphs[s].inputs[0])
                     ready[s].record(copy_stream)
                 with torch.cuda.stream(comp_stream):
                     comp_stream.wait_event(ready[s])
+                    comp_stream.wait_event(freed[s])
                     res = graphs[s]()
+                    done[s].record(comp_stream)
+                with torch.cuda.stream(d2h_stream):
+                    d2h_stream.wait_event(done[s])
                     out_host[s].copy_(res, non_blocking=True)
-                    freed[s].record(comp_stream)
+                    freed[s].record(d2h_stream)
+            d2h_stream.synchronize()
             comp_stream.synchronize()
 
         for s in range(2):
+            done[s].record(comp_stream)
             freed[s].record(comp_stream)
         e2e_run(max(2, min(W, 3)))
         torch.cuda.synchronize()
@@ -458,7 +469,7 @@ def run_ours(args, rank, world, local):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, **CFG, "global_slices_per_step": world * nb, "parallelism": f"dp{world} (slices sharded, no collective)",
                    "l2": f"inputs larger than L2: {alg['K'] / 1e6:.0f} MB k-space per tensor per step", "regulariser": "identity (outside the hot path)",
-                   "launch": f"whole step captured in one CUDA graph, slices split over {CFG['streams']} streams inside it"},
+                   "launch": "whole step captured in one CUDA graph" + (f", slices split over {CFG['streams']} streams inside it" if CFG["streams"] > 1 else ", one stream")},
         "clocks": clocks,
         "e2e": {"value": world * nb * K / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "h2d": f"sampled k-space rows only ({h2d_bytes / 1e6:.0f} of {mk_host.numel() * 4 / 1e6:.0f} MB dense), read from pinned memory by "
