@@ -39,8 +39,9 @@ sys.path.insert(0, str(ROOT))
 WORKLOAD = "XF-VarNet 12-cascade SENSE/DC hot path, 10-coil 15-frame 200x200 cine slices"
 # streams: the slice batch can be split over CUDA streams inside the graph (pipeline.varnet_hot_path_streams); measured
 # (tools/batch_sweep.py, profiles/r2_batch_sweep.txt): two streams win at 4 slices per step (1058 vs 1004 slices/s), one stream
-# wins from 8 slices on (16 slices: 1122 vs 1041)
-CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=16, streams=1, upload_sms=4)
+# wins from 8 slices on (16 slices: 1122 vs 1041); 150 coil images per slice on 148 persistent CTAs always leave a ragged last
+# round, so larger batches amortise it: 1122 / 1137 / 1148 slices/s at 16 / 24 / 32 slices per step
+CFG = dict(t=15, c=10, h=200, w=200, cascades=12, slices_per_gpu_step=32, streams=1, upload_sms=4)
 for _k, _e in (("upload_sms", "B2S_BENCH_UPLOAD_SMS"), ("streams", "B2S_BENCH_STREAMS"), ("slices_per_gpu_step", "B2S_BENCH_SLICES")):
     if os.environ.get(_e):                          # dev overrides
         CFG[_k] = int(os.environ[_e])

@@ -56,7 +56,9 @@ for r in rows[2:]:
         float(r[hdr.index("dram__bytes_write.sum")]) * f[units[hdr.index("dram__bytes_write.sum")]]
     md.append(f"| **dram read + write** | {t / 1e6:.1f} | MB per launch |")
     nb = int(sys.argv[4]) if len(sys.argv) > 4 else 4          # slices per launch of the capture (tools/prof_target.py argument)
-    if "EpiDCStage" in name or "EpiKspace<200, 200, 2>" in name: traffic.update(sens_expand_dc_dram_bytes_per_launch=t, sens_expand_dc_algorithmic_bytes=104000000 * nb)
+    if "EpiDCStage" in name or "EpiKspace<200, 200, 2>" in name:     # one sens_expand + soft-DC call = packed whole-image kernel + half-split tail
+        traffic["sens_expand_dc_dram_bytes_per_launch"] = traffic.get("sens_expand_dc_dram_bytes_per_launch", 0.0) + t
+        traffic["sens_expand_dc_algorithmic_bytes"] = 104000000 * nb
     if "EpiReduce" in name: traffic.update(sens_reduce_dram_bytes_per_launch=t, sens_reduce_algorithmic_bytes=56000000 * nb)
     if "EpiPlain" in name: traffic.update(fft2c_dram_bytes_per_launch=t, fft2c_algorithmic_bytes=96000000 * nb)
     if "normal_warp" in name: traffic.update(normal_op_dram_bytes_per_launch=t, normal_op_algorithmic_bytes=12800000 * nb)
