@@ -408,6 +408,25 @@ def run_ours(args, rank, world, local):
         torch.cuda.synchronize()
         img_sec = bdist.max_over_ranks(f0.elapsed_time(f1) * 1e-3, dev)
 
+        # ---- b = 1 per call (the reference's SensitivityModel assumes it, varnet.py:65; what `gpu_reference` times): one slice per
+        #      graph replay, k-space path and image-domain path - the per-call latency a user of the drop-in sees
+        b1 = {}
+        for name, fn in (("kspace_path", lambda k_, m_: pipeline.varnet_hot_path(k_, m_, v, CFG["cascades"], xf=True)),
+                         ("image_domain_path", lambda k_, m_: pipeline.varnet_hot_path_image_domain(k_, m_, v, CFG["cascades"], xf=True))):
+            g1 = pipeline.Graphed(fn, mk[:1].contiguous(), mask[:1].contiguous(), warmup=2)
+            for _ in range(3):
+                g1()
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(20):
+                g1()
+            q1.record()
+            torch.cuda.synchronize()
+            ms1 = bdist.max_over_ranks(q0.elapsed_time(q1) / 20, dev)
+            b1[name] = {"ms_per_slice": ms1, "slices_per_sec": world * 1e3 / ms1}
+            del g1
+
         # ---- BASELINE configs[2] shape: CineNet (CRNN) SENSE/CG hot path, 10 iterations x CG 4, 20 coils, 25 frames;
         #      b = 1 per call (reference semantics), four independent slices on four streams inside one CUDA graph
         from deep_cine_cardiac_mri_b200 import synth
@@ -489,6 +508,8 @@ def run_ours(args, rank, world, local):
                     "algorithmic_bytes": dc_alg, "us": dc_pair_sec * 1e6,
                     "what": "sens_reduce + sens_expand/soft-DC pair (3K + 2I + 2S), median of 20 eager pairs, CUDA events around both launches"},
         "gpu_reference": gpu_ref,
+        "b1_per_call": {**b1, "what": "one slice per call (b = 1, the reference's calling convention and what gpu_reference times), one CUDA-graph replay per slice, "
+                                      "device-timed, inputs resident"},
         "op_sweep": sweep,
         "cinenet_hot_path": {"value": world * n_cine / cine_sec, "unit": UNIT, "ms_per_slice": cine_sec / n_cine * 1e3,
                              "workload": "CineNet SENSE/CG hot path, 10 iterations x CG 4 (50 normal-operator applications), "
