@@ -7,7 +7,7 @@ using namespace b2s;
 
 template <class P> static int launch_warp(const NormalArgs& a, long long items, cudaStream_t st) {
   B2S_CUDA(cudaFuncSetAttribute(normal_warp_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES));
-  const unsigned blocks = (unsigned)((items + P::WARPS - 1) / P::WARPS);
+  const unsigned blocks = (unsigned)((items + P::ITEMS - 1) / P::ITEMS);
   normal_warp_kernel<P><<<blocks, P::NT, P::SMEM_BYTES, st>>>(a, items);
   return check_launch("normal_warp_kernel");
 }
@@ -24,6 +24,11 @@ static int launch_normal(const float* x, const float* sens, const uint8_t* mask,
   if (items == 0) return B2S_OK;
   if (items > 0x7fffffffLL) return fail(B2S_EUNSUPPORTED, "b2s_normal_op: too many frames");
   const cudaStream_t st = (cudaStream_t)stream;
+  // small launches (fewer work items than half the warps the GPU holds, e.g. one 15-frame slice per call): two warps share an
+  // item, each takes half of the coils, the partial coil sums are added in a fixed order
+  int sms = 148;
+  { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  if (h == 200 && w == 200 && c >= 2 && items * 2 <= (long long)sms * 12) return launch_warp<NormalWarpPlan<200, 200, 4, 3, 2>>(a, items, st);
   if (h == 200) return w == 200 ? launch_warp<NormalWarpPlan<200, 200, 3, 4>>(a, items, st) : launch_warp<NormalWarpPlan<200, 0, 3, 4>>(a, items, st);
   return w == 256 ? launch_warp<NormalWarpPlan<256, 256, 4, 2>>(a, items, st) : launch_warp<NormalWarpPlan<256, 0, 4, 2>>(a, items, st);
 }

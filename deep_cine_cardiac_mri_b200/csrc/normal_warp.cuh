@@ -49,9 +49,12 @@ struct NormalArgs {
 
 struct alignas(16) nquad { float ra, rb, ia, ib; };
 
-template <int H_, int W_, int WARPS_, int CTAS_> struct NormalWarpPlan {
+template <int H_, int W_, int WARPS_, int CTAS_, int SPLIT_ = 1> struct NormalWarpPlan {
   static constexpr int H = H_, G = H_ / 8, XC = 4, WFIX = W_;
-  static constexpr int WARPS = WARPS_, NT = 32 * WARPS_, CTAS = CTAS_;   // CTAS: resident CTAs per SM the registers are budgeted for
+  static constexpr int WARPS = WARPS_, NT = 32 * WARPS_, CTAS = CTAS_;
+  static constexpr int SPLIT = SPLIT_;                        // warps that share one work item, each taking 1/SPLIT of the coils (small launches:
+  static constexpr int ITEMS = WARPS_ / SPLIT_;               // fills the GPU when b*t*w/4 items are fewer than the resident warps); items per CTA
+  static_assert(WARPS_ % SPLIT_ == 0, "whole items per CTA");   // CTAS: resident CTAs per SM the registers are budgeted for
   static constexpr int NP = (G + 1) / 2;                      // quads (pairs of adjacent g) per (m, xl)
   static constexpr int EPQ = 8 * XC + 4;                      // quads per pair-block of E; 36 = 4 mod 8: step 2 conflict-free
   // per warp, in 8-byte units
@@ -252,22 +255,28 @@ __global__ void __launch_bounds__(P::NT, P::CTAS) normal_warp_kernel(const Norma
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   nw_build_tables<P>(smem, tid, P::NT);
   __syncthreads();                                        // the only CTA barrier
-  const long long item = (long long)blockIdx.x * P::WARPS + warp;
-  if (item >= n_items) return;
+  const int part = warp % P::SPLIT;
+  const long long item = (long long)blockIdx.x * P::ITEMS + warp / P::SPLIT;
+  if (item >= n_items) return;                            // (all SPLIT warps of an item leave together)
   cfloat* ws = smem + warp * P::WARP_ELEMS;
   const int w = nw_width<P>(a);
   const int groups = w / P::XC;
   const long long bt = item / groups;
   const int x0 = (int)(item - bt * groups) * P::XC;
   const size_t hw = (size_t)P::H * w;
-  const cfloat* sp = a.sens + (size_t)(bt / a.T) * a.C * hw + (size_t)(lane >> 2) * w + x0 + (lane & 3);
+  const int c0 = (int)((long long)part * a.C / P::SPLIT), c1 = (int)((long long)(part + 1) * a.C / P::SPLIT);   // this warp's coils
+  const cfloat* sp = a.sens + ((size_t)(bt / a.T) * a.C + c0) * hw + (size_t)(lane >> 2) * w + x0 + (lane & 3);
   nw_stage<P>(a, ws, bt, x0, lane);
   float accr[P::G], acci[P::G];
   cfloat sv[P::G];
-  nw_init_acc<P>(a, bt, x0, lane, accr, acci);
+  if (part == 0) nw_init_acc<P>(a, bt, x0, lane, accr, acci);
+  else {
+#pragma unroll
+    for (int k = 0; k < P::G; ++k) { accr[k] = 0.f; acci[k] = 0.f; }
+  }
   __syncwarp();                                           // mask factors visible to the warp
 #pragma unroll 1
-  for (int c = 0; c < a.C; ++c) {
+  for (int c = c0; c < c1; ++c) {
     nw_step1<P>(a, ws, smem, sp, lane, sv);
     sp += hw;
     __syncwarp();
@@ -279,6 +288,19 @@ __global__ void __launch_bounds__(P::NT, P::CTAS) normal_warp_kernel(const Norma
     __syncwarp();
     nw_step3<P>(ws, lane, sv, accr, acci);
     __syncwarp();
+  }
+  if (P::SPLIT > 1) {                                     // partial coil sums of the item's other warps -> warp `part == 0` (fixed order)
+    if (part != 0) {
+#pragma unroll
+      for (int k = 0; k < P::G; ++k) ws[P::E_OFF + 32 * k + lane] = make_c(accr[k], acci[k]);   // (the exchange buffer is free now)
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / P::SPLIT), "r"(32 * P::SPLIT) : "memory");   // named barrier of this item's warps
+    if (part != 0) return;
+    for (int q = 1; q < P::SPLIT; ++q) {
+      const cfloat* other = ws + q * P::WARP_ELEMS + P::E_OFF;
+#pragma unroll
+      for (int k = 0; k < P::G; ++k) { const cfloat v = other[32 * k + lane]; accr[k] += v.x; acci[k] += v.y; }
+    }
   }
   float dsum = nw_finish<P>(a, ws, bt, x0, lane, accr, acci, *a.vptr);
   if (a.dot_part) {                                       // fixed-order butterfly over the warp: bit-reproducible partials
@@ -309,11 +331,21 @@ void normal_warp_emulate(const NormalArgs& a, long long n_bt) {
       nw_stage<P>(a, ws, bt, x0, lane);
       nw_init_acc<P>(a, bt, x0, lane, accr[lane], acci[lane]);
     }
-    for (int c = 0; c < a.C; ++c) {
-      for (int lane = 0; lane < 32; ++lane) { nw_step1<P>(a, ws, smem, sp[lane], lane, sv[lane]); sp[lane] += hw; }
-      for (int task = 0; task < P::TASKS2; ++task) nw_step2<P>(ws, smem, task);
-      for (int lane = 0; lane < 32; ++lane) nw_step3<P>(ws, lane, sv[lane], accr[lane], acci[lane]);
+    float (*pr)[P::G] = new float[32][P::G];
+    float (*pi)[P::G] = new float[32][P::G];
+    for (int part = 0; part < P::SPLIT; ++part) {           // the item's warps one after the other, partial sums added in warp order
+      const int c0 = (int)((long long)part * a.C / P::SPLIT), c1 = (int)((long long)(part + 1) * a.C / P::SPLIT);
+      float (*ar)[P::G] = part == 0 ? accr : pr;
+      float (*ai)[P::G] = part == 0 ? acci : pi;
+      if (part > 0) for (int lane = 0; lane < 32; ++lane) for (int k = 0; k < P::G; ++k) { ar[lane][k] = 0.f; ai[lane][k] = 0.f; }
+      for (int c = c0; c < c1; ++c) {
+        for (int lane = 0; lane < 32; ++lane) nw_step1<P>(a, ws, smem, sp[lane] + (size_t)c * hw, lane, sv[lane]);
+        for (int task = 0; task < P::TASKS2; ++task) nw_step2<P>(ws, smem, task);
+        for (int lane = 0; lane < 32; ++lane) nw_step3<P>(ws, lane, sv[lane], ar[lane], ai[lane]);
+      }
+      if (part > 0) for (int lane = 0; lane < 32; ++lane) for (int k = 0; k < P::G; ++k) { accr[lane][k] += pr[lane][k]; acci[lane][k] += pi[lane][k]; }
     }
+    delete[] pr; delete[] pi;
     float dsum = 0.f;
     for (int lane = 0; lane < 32; ++lane) dsum += nw_finish<P>(a, ws, bt, x0, lane, accr[lane], acci[lane], *a.vptr);
     if (a.dot_part) a.dot_part[item] = dsum;

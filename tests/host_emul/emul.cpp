@@ -138,7 +138,8 @@ extern "C" int emu_normal_warp(const float* x, const float* sens, const uint8_t*
   NormalArgs a; a.x = (const cfloat*)x; a.sens = (const cfloat*)sens; a.mask = mask; a.vptr = v; a.out = (cfloat*)out;
   a.T = t; a.C = c; a.W = w; a.mode = mode; a.ssq = ssq; a.bref = (const cfloat*)bref; a.dot_part = nullptr;
   const long long n = (long long)b * t;
-  if (h == 200) { if (fixed) normal_warp_emulate<NormalWarpPlan<200, 200, 3, 4>>(a, n); else normal_warp_emulate<NormalWarpPlan<200, 0, 3, 4>>(a, n); }
+  if (h == 200 && fixed == 2) normal_warp_emulate<NormalWarpPlan<200, 200, 4, 3, 2>>(a, n);        // two warps per item, half of the coils each
+  else if (h == 200) { if (fixed) normal_warp_emulate<NormalWarpPlan<200, 200, 3, 4>>(a, n); else normal_warp_emulate<NormalWarpPlan<200, 0, 3, 4>>(a, n); }
   else          { if (fixed) normal_warp_emulate<NormalWarpPlan<256, 256, 4, 2>>(a, n); else normal_warp_emulate<NormalWarpPlan<256, 0, 4, 2>>(a, n); }
   return 0;
 }

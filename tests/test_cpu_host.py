@@ -161,11 +161,11 @@ def test_emulated_sense_operators(emu, variant, hw):
     assert rel(out, want_s) <= 1e-6
 
 
-@pytest.mark.parametrize("h,w,fixed", [(200, 200, 1), (200, 200, 0), (256, 256, 1), (200, 36, 0), (256, 12, 0)])
+@pytest.mark.parametrize("h,w,fixed", [(200, 200, 1), (200, 200, 0), (200, 200, 2), (256, 256, 1), (200, 36, 0), (256, 12, 0)])
 def test_emulated_warp_private_normal_operator(emu, h, w, fixed):
     """normal_warp.cuh (product kernel of b2s_normal_op / b2s_normal_dc) executed lane by lane on the CPU: both modes
     (normal operator; b2s_normal_dc == A^H[DC(A x, ref)], one VarNet cascade without materialising k-space), both
-    heights, compile-time and run-time widths."""
+    heights, compile-time and run-time widths, and the coil-split plan of small launches (fixed == 2: two warps per item)."""
     b, t, c = 1, 2, 3
     cs = G.sense_case(11, b, t, c, h, w)
     d = {k: (a.astype(np.float64) if getattr(a, "dtype", None) == np.float32 and a.ndim else a) for k, a in cs.items()}
