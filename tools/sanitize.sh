@@ -19,6 +19,9 @@ for (b, t, c, h, w) in ((1, 2, 2, 200, 200), (1, 1, 2, 256, 256), (1, 2, 3, 18, 
         if ops.normal_op_supported(h, w):
             ops.raw_normal_op(x, s, m, v)
             ops.raw_normal_dc(x, s, m, v, s.pow(2).sum(dim=(1, 4)).contiguous(), img)
+            ops.raw_normal_dc(x, s, m, v, s.pow(2).sum(dim=(1, 4)).contiguous(), img, magnitude=True)
+            from deep_cine_cardiac_mri_b200 import blocks
+            blocks._cg_inference(x, img, m.view(b, t, 1, h, 1, 1), s, v, 2)     # fused CG iteration (normal_op_dot, cg_update, cg_direction)
         for fam in ("half", "packed"):          # both kernel families of the fused plan sizes
             ops.set_fused_path(fam)
             ops.raw_sens_expand(img, s, 2, ref, m, v); ops.raw_sens_expand(img, s, 0, ref, m, v); ops.raw_sens_reduce(k, s)
